@@ -1,0 +1,158 @@
+// Stage-level C-ABI entry points (include/dtp.h, "operator entry points"): one call = one kernel family on borrowed
+// device pointers. Used by the parity tests and the roofline isolation benches; the pipeline (runtime.cu) calls the
+// same kernels through the C++ interfaces.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/dtp.h"
+#include "gemm_tc.h"
+#include "kernels.h"
+
+using namespace dtp;
+
+namespace {
+float* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+char g_err[512] = "";
+
+int ensure_ws(size_t bytes) {
+    if (bytes <= g_ws_bytes) return 0;
+    if (g_ws) cudaFree(g_ws);
+    g_ws = nullptr;
+    g_ws_bytes = 0;
+    if (cudaMalloc(&g_ws, bytes) != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "workspace cudaMalloc(%zu) failed", bytes);
+        return -1;
+    }
+    g_ws_bytes = bytes;
+    return 0;
+}
+
+int finish(GemmOp& op, int rc_setup, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags,
+           float alpha, int hw_out, cudaStream_t st) {
+    if (rc_setup) {
+        snprintf(g_err, sizeof(g_err), "gemm setup: %s", gemm_last_error());
+        return rc_setup;
+    }
+    op.p.bias = bias;
+    op.p.residual = reinterpret_cast<const __half*>(residual);
+    op.p.ldr = ldr;
+    op.p.out = out;
+    if (ldc > 0) op.p.ldc = ldc;
+    op.p.flags |= flags;
+    op.p.alpha = alpha;
+    op.p.hw_out = hw_out;
+    if (ensure_ws(gemm_workspace_bytes(&op))) return -1;
+    op.p.workspace = g_ws;
+    int r = gemm_launch(&op, st);
+    if (r) snprintf(g_err, sizeof(g_err), "gemm launch: %s", gemm_last_error());
+    return r;
+}
+}  // namespace
+
+extern "C" {
+
+const char* dtp_ops_last_error(void) { return g_err; }
+
+int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, int K1, int M, const void* Wt, int ldw,
+                  int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
+                  int hw_out, int BN, int splits, void* stream) {
+    GemmOp op;
+    if (BN <= 0) gemm_pick_config((M + 127) / 128, N, (K0 + 63) / 64 + (A1 ? (K1 + 63) / 64 : 0), flags, &BN, &splits);
+    int r = gemm_setup_linear(&op, (const __half*)A0, lda0, K0, (const __half*)A1, lda1, K1, M, (const __half*)Wt, ldw,
+                              N, BN, splits);
+    return finish(op, r, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
+}
+
+int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int H, int W, const void* Wt, int Cout,
+                   const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
+                   int hw_out, int BN, int splits, void* stream) {
+    GemmOp op;
+    if (BN <= 0) {
+        GemmOp probe;
+        // tile count depends on the pixel-box decomposition; set up once to learn grid_m
+        int r0 = gemm_setup_conv3x3(&probe, (const __half*)A0, C0, (const __half*)A1, C1, Nimg, H, W,
+                                    (const __half*)Wt, Cout, 128, 1);
+        if (r0) return finish(probe, r0, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
+        gemm_pick_config(probe.grid_m, Cout, probe.p.num_kb, flags, &BN, &splits);
+    }
+    int r = gemm_setup_conv3x3(&op, (const __half*)A0, C0, (const __half*)A1, C1, Nimg, H, W, (const __half*)Wt, Cout,
+                               BN, splits);
+    return finish(op, r, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
+}
+
+int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
+               long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
+               long long out_zs2, float alpha, int flags, int BN, void* stream) {
+    GemmOp op;
+    if (BN <= 0) {
+        int sp;
+        gemm_pick_config(((M + 127) / 128) * nz1 * nz2, N, (K + 63) / 64, b_mn ? GEMM_B_MN : 0, &BN, &sp);
+    }
+    int r = gemm_setup_batched(&op, (const __half*)A, lda, a_zs1, a_zs2, (const __half*)B, ldb, b_zs1, b_zs2, b_mn, M, N,
+                               K, nz1, nz2, BN);
+    op.p.out_zs1 = out_zs1;
+    op.p.out_zs2 = out_zs2;
+    return finish(op, r, nullptr, nullptr, 0, out, ldc, flags, alpha, 0, (cudaStream_t)stream);
+}
+
+int dtp_op_groupnorm(const void* x0, int C0, const void* x1, int C1, int Nimg, int HW, int groups, const float* gamma,
+                     const float* beta, float eps, int silu, void* out, void* stream) {
+    const int chunks = gn_num_chunks(HW, C0 + C1);
+    if (ensure_ws(sizeof(float) * 2 * groups * chunks * Nimg)) return -1;
+    return launch_groupnorm((const __half*)x0, C0, (const __half*)x1, C1, Nimg, HW, groups, gamma, beta, eps, silu,
+                            (__half*)out, g_ws, (cudaStream_t)stream);
+}
+
+int dtp_op_layernorm(const void* x, int rows, int C, const float* gamma, const float* beta, float eps, void* out,
+                     void* stream) {
+    return launch_layernorm((const __half*)x, rows, C, gamma, beta, eps, (__half*)out, (cudaStream_t)stream);
+}
+
+int dtp_op_softmax(void* x, long long rows, int cols, int ld, void* stream) {
+    return launch_softmax_rows((__half*)x, rows, cols, ld, (cudaStream_t)stream);
+}
+
+int dtp_op_attn_small(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int nq,
+                      int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
+                      const int* kv_index, float scale, void* stream) {
+    return launch_attn_small((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, (__half*)out, ldo, nq,
+                             nkv, heads, d, batch, q_bs, kv_bs, o_bs, kv_index, scale, (cudaStream_t)stream);
+}
+
+int dtp_op_upsample2x(const void* x, int Nimg, int H, int W, int C, void* out, void* stream) {
+    return launch_upsample2x((const __half*)x, Nimg, H, W, C, (__half*)out, (cudaStream_t)stream);
+}
+
+int dtp_op_im2col_s2(const void* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, void* out,
+                     void* stream) {
+    return launch_im2col_s2((const __half*)x, Nimg, H, W, C, pad_lo, Ho, Wo, (__half*)out, (cudaStream_t)stream);
+}
+
+int dtp_op_ddim_step(const float* eps3, const float* latents_in, float* latents_out, int B, int chw, float cfg, float tg,
+                     float alpha_t, float alpha_prev, void* stream) {
+    return launch_guidance_ddim(eps3, latents_in, latents_out, B, chw, cfg, tg, alpha_t, alpha_prev,
+                                (cudaStream_t)stream);
+}
+
+int dtp_op_pack_unet_input(const float* latents, const float* mask3, const float* masked3, int B, int hw, void* out,
+                           void* stream) {
+    return launch_pack_unet_input(latents, mask3, masked3, B, hw, (__half*)out, (cudaStream_t)stream);
+}
+
+int dtp_op_nchw_to_nhwc_pad(const float* x, int Nimg, int C, int HW, int Cpad, float scale, void* out, void* stream) {
+    return launch_nchw_to_nhwc_pad(x, Nimg, C, HW, Cpad, scale, (__half*)out, (cudaStream_t)stream);
+}
+
+int dtp_op_canvas_preprocess(const float* canvas, const float* brush, int B, int R, int pad, float* masked_img,
+                             float* mask, float* ctx_img, float* ctx_mask, float* scratch, void* stream) {
+    return launch_canvas_preprocess(canvas, brush, B, R, pad, masked_img, mask, ctx_img, ctx_mask, scratch,
+                                    (cudaStream_t)stream);
+}
+
+int dtp_op_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
+                     void* stream) {
+    return launch_composite(canvas, raw, B, R, out_f32, out_u8hwc, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// tcgen05 tensor-core contraction for the stamp path (sm_100a only).
+//
+//   D[M,N] = alpha * A[M,K] * W[N,K]^T (+ bias) -> activation -> (+ residual)      fp16 operands, fp32 TMEM accumulation
+//
+// One kernel family serves every dense contraction of the UNet / VAE / image encoder:
+//   * linear layers and 1x1 convs (A = activation rows; NHWC == (pixels, C));
+//   * 3x3 stride-1 pad-1 convs as implicit GEMM: the A tile of tap (ky,kx) is a shifted 4-D TMA box of the NHWC
+//     activation; out-of-bounds pixels are zero-filled by TMA, which IS the conv zero padding;
+//   * skip-concat inputs (torch.cat([h, skip], 1) in the diffusers up blocks) read as two sources, never
+//     materialised: the channel blocks of a tap come first from source 0, then from source 1;
+//   * batched products for attention (scores = Q K^T, out = P V) with (head, sample) batch coordinates carried as
+//     TMA dimensions 2 and 3, V consumed as an MN-major B operand (no transpose pass).
+// Replaces the TensorRT conv/GEMM tactics behind trt_inference/utilities.py:252 (Engine.infer) for the graphs
+// described by trt_inference/models.py:1017-1420.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dtp {
+
+enum GemmFlags : int {
+    EPI_NONE = 0,
+    EPI_GELU = 1 << 0,          // erf GELU on (acc*alpha + bias)
+    EPI_QUICKGELU = 1 << 1,     // x * sigmoid(1.702 x)   (CLIP MLP)
+    EPI_SILU = 1 << 2,          // x * sigmoid(x)
+    EPI_GEGLU = 1 << 3,         // out[:, j] = a_j * gelu(g_j); weight rows interleaved per 32-column chunk (16 a | 16 g)
+    EPI_BIAS_M = 1 << 4,        // bias indexed by output row
+    EPI_OUT_F32_NCHW = 1 << 5,  // fp32 output, NCHW with hw_out pixels per image
+    EPI_IMG01 = 1 << 6,         // out = clamp(x / 2 + 0.5, 0, 1)   (inpaint_pipeline.py:148)
+    EPI_OUT_F32 = 1 << 7,       // fp32 row-major output
+    GEMM_B_MN = 1 << 8,         // B operand is MN-major in global memory: B[K, N] row-major (V of attention)
+};
+
+struct GemmParams {
+    int M, N;          // output rows per batch entry / output columns of the contraction
+    int num_kb;        // number of 64-wide k blocks (all taps)
+    int mode;          // 0 = linear, 1 = conv3x3 (stride 1, pad 1)
+    int H, W, Nimg;    // conv: spatial extent (input == output) and image count
+    int bw, bh, bn;    // conv: pixel extents of the A box
+    int tiles_x, tiles_y;
+    int rows_valid;    // conv: bw*bh*bn (<= 128) rows of the tile that map to pixels
+    int cblocks0;      // 64-channel blocks (per tap) that come from source 0
+    int cblocks;       // 64-channel blocks per tap (source 0 + source 1); linear: == num_kb
+    int splits;        // split-K factor; > 1 writes fp32 partials to workspace and a finalize kernel runs the epilogue
+    int nz1, nz2;      // batch extents (heads, samples); grid.z = nz1 * nz2 * splits
+    int a_batched;     // A map uses (z1,z2) as coords 2,3
+    int b_batched;     // B map uses (z1,z2) as coords 2,3
+    long long out_zs1, out_zs2;  // output offset (elements) per z1 / z2
+    int flags;         // GemmFlags
+    int hw_out;        // EPI_OUT_F32_NCHW: pixels per image
+    int ldc;           // output row stride (elements)
+    int ldr;           // residual row stride (elements)
+    float alpha;       // multiplies acc before bias
+    const float* bias;        // [N] fp32 (or [M] with EPI_BIAS_M), nullable
+    const __half* residual;   // [M, ldr] fp16, nullable
+    void* out;                // fp16 [M, ldc] (default) / fp32 variants
+    float* workspace;         // [batch*splits, Mpad, N] fp32
+};
+
+struct GemmOp {
+    CUtensorMap mapA0, mapA1, mapB;
+    GemmParams p;
+    int BN;      // 32, 64, 128 or 256
+    int grid_m;  // number of 128-row tiles
+};
+
+// Tensor-map helper (driver entry point resolved at run time; no link-time libcuda dependency). 0 on success.
+int make_map_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                const uint32_t box[4]);
+
+// Linear problem: A0 [M, K0] (row stride lda0) and optional A1 [M, K1] (K0 % 64 == 0 when A1 is used);
+// Wt [N, K0+K1] row-major (row stride ldw). Strides in elements, multiples of 8.
+int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
+                      const __half* Wt, int ldw, int N, int BN, int splits);
+// 3x3/s1/p1 conv over NHWC activations: sources (Nimg,H,W,C0) and optional (Nimg,H,W,C1), C0,C1 % 64 == 0;
+// Wt [Cout, 9*(C0+C1)] with k = (ky*3+kx)*(C0+C1) + c.
+int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, int C1, int Nimg, int H, int W,
+                       const __half* Wt, int Cout, int BN, int splits);
+// Batched product over (z1 in [0,nz1), z2 in [0,nz2)):  D_z[M,N] = A_z[M,K] * B_z^T
+//   A_z = A + z1*a_zs1 + z2*a_zs2 (row stride lda);  K-major B_z[N,K] = B + z1*b_zs1 + z2*b_zs2 (row stride ldb),
+//   or with b_mn: B_z[K,N] row-major (row stride ldb).  All strides in elements, multiples of 8.
+int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, long long a_zs2, const __half* B, int ldb,
+                       long long b_zs1, long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, int BN);
+
+int gemm_launch(const GemmOp* op, cudaStream_t stream);
+size_t gemm_workspace_bytes(const GemmOp* op);
+// heuristic tile / split selection for a problem with `mtiles` 128-row tiles
+void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits);
+const char* gemm_last_error();
+
+}  // namespace dtp

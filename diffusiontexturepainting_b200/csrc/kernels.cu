@@ -1,0 +1,789 @@
+// HBM-bound kernels of the stamp path. See kernels.h.
+#include "kernels.h"
+
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace dtp {
+
+static char g_kerr[256] = "";
+const char* kernels_last_error() { return g_kerr; }
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_kerr, sizeof(g_kerr), "%s: %s", what, cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
+struct alignas(16) Half8 {
+    __half2 h[4];
+};
+__device__ __forceinline__ Half8 ld8(const __half* p) {
+    Half8 r;
+    *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+__device__ __forceinline__ void st8(__half* p, const Half8& v) {
+    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
+}
+__device__ __forceinline__ void unpack8(const Half8& v, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(v.h[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ Half8 pack8(const float (&f)[8]) {
+    Half8 v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm: (1) per-chunk partial sums, (2) finalize mean / rstd in double, (3) apply (+SiLU)
+// ------------------------------------------------------------------------------------------------------------
+int gn_num_chunks(int HW, int C) {
+    long long elems = static_cast<long long>(HW) * C;
+    long long chunks = elems / 16384;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 512) chunks = 512;
+    if (chunks > HW) chunks = HW;
+    return static_cast<int>(chunks);
+}
+size_t gn_ws_floats(int Nimg, int HW, int C, int groups) {
+    return static_cast<size_t>(Nimg) * gn_num_chunks(HW, C) * groups * 2 + static_cast<size_t>(Nimg) * groups * 2;
+}
+
+// grid (chunks, Nimg); block = CV * rows_per_iter threads, CV = C / 8
+__global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                                int groups, int chunks, float* __restrict__ partial) {
+    extern __shared__ float2 sm_acc[];  // [rows_per_iter][C]
+    const int C = C0 + C1;
+    const int CV = C >> 3;
+    const int cv = threadIdx.x % CV;
+    const int prow = threadIdx.x / CV;
+    const int rows_per_iter = blockDim.x / CV;
+    const int n = blockIdx.y;
+    const int ppc = (HW + chunks - 1) / chunks;
+    const int p0 = blockIdx.x * ppc;
+    const int p1 = min(HW, p0 + ppc);
+    const int c = cv * 8;
+    const __half* src;
+    int ldc;
+    if (c < C0) {
+        src = x0 + static_cast<long long>(n) * HW * C0 + c;
+        ldc = C0;
+    } else {
+        src = x1 + static_cast<long long>(n) * HW * C1 + (c - C0);
+        ldc = C1;
+    }
+    float s[8], ss[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.0f;
+    for (int p = p0 + prow; p < p1; p += rows_per_iter) {
+        float f[8];
+        unpack8(ld8(src + static_cast<long long>(p) * ldc), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s[e] += f[e];
+            ss[e] += f[e] * f[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm_acc[prow * C + c + e] = make_float2(s[e], ss[e]);
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        const int cpg = C / groups;
+        float a = 0.0f, b = 0.0f;
+        for (int r = 0; r < rows_per_iter; ++r)
+            for (int cc = 0; cc < cpg; ++cc) {
+                const float2 t = sm_acc[r * C + threadIdx.x * cpg + cc];
+                a += t.x;
+                b += t.y;
+            }
+        float* dst = partial + ((static_cast<long long>(n) * chunks + blockIdx.x) * groups + threadIdx.x) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+}
+
+// grid Nimg; block groups
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, double count, float eps,
+                                   float* __restrict__ stats) {
+    const int n = blockIdx.x, g = threadIdx.x;
+    if (g >= groups) return;
+    double a = 0.0, b = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) {
+        const float* src = partial + ((static_cast<long long>(n) * chunks + ch) * groups + g) * 2;
+        a += static_cast<double>(src[0]);
+        b += static_cast<double>(src[1]);
+    }
+    const double mean = a / count;
+    double var = b / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(n * groups + g) * 2] = static_cast<float>(mean);
+    stats[(n * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+__global__ void __launch_bounds__(256)
+    gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
+                    long long total_vec, const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int silu, __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total_vec) return;
+    const int C = C0 + C1;
+    const int CV = C >> 3;
+    const int cv = static_cast<int>(i % CV);
+    const long long pix = i / CV;  // n*HW + p
+    const int n = static_cast<int>(pix / HW);
+    const int c = cv * 8;
+    const int cpg = C / groups;
+    float f[8];
+    if (c < C0)
+        unpack8(ld8(x0 + pix * C0 + c), f);
+    else
+        unpack8(ld8(x1 + pix * C1 + (c - C0)), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c + e) / cpg;
+        const float mean = __ldg(stats + (n * groups + g) * 2);
+        const float rstd = __ldg(stats + (n * groups + g) * 2 + 1);
+        float y = (f[e] - mean) * rstd * __ldg(gamma + c + e) + __ldg(beta + c + e);
+        if (silu) y = silu_f(y);
+        f[e] = y;
+    }
+    st8(out + pix * C + c, pack8(f));
+}
+
+int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
+                     const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
+                     cudaStream_t st) {
+    if (x1 == nullptr) C1 = 0;
+    const int C = C0 + C1;
+    if ((C0 % 8) || (C1 % 8) || (C % groups) || groups > 256) {
+        snprintf(g_kerr, sizeof(g_kerr), "groupnorm: unsupported channels C0=%d C1=%d groups=%d", C0, C1, groups);
+        return -1;
+    }
+    const int CV = C / 8;
+    if (CV > 1024) {
+        snprintf(g_kerr, sizeof(g_kerr), "groupnorm: C=%d too large", C);
+        return -1;
+    }
+    const int chunks = gn_num_chunks(HW, C);
+    int rows_per_iter = 256 / CV;
+    if (rows_per_iter < 1) rows_per_iter = 1;
+    int threads = CV * rows_per_iter;
+    if (threads < groups) {
+        rows_per_iter = (groups + CV - 1) / CV;
+        threads = CV * rows_per_iter;
+    }
+    float* partial = stats_ws;
+    float* stats = stats_ws + static_cast<size_t>(Nimg) * chunks * groups * 2;
+    const size_t smem = static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
+    gn_stats_kernel<<<dim3(chunks, Nimg), threads, smem, st>>>(x0, C0, x1, C1, HW, groups, chunks, partial);
+    if (check_launch("gn_stats")) return -1;
+    gn_finalize_kernel<<<Nimg, ((groups + 31) / 32) * 32, 0, st>>>(partial, chunks, groups,
+                                                                    static_cast<double>(HW) * (C / groups), eps, stats);
+    if (check_launch("gn_finalize")) return -1;
+    const long long total_vec = static_cast<long long>(Nimg) * HW * CV;
+    gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, st>>>(x0, C0, x1, C1, HW, groups, total_vec,
+                                                                                   stats, gamma, beta, silu, out);
+    return check_launch("gn_apply");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass variance
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, __half* __restrict__ out) {
+    constexpr int MAXV = 8;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int CV = C >> 3;
+    const __half* src = x + static_cast<long long>(row) * C;
+    float f[MAXV][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int v = lane + j * 32;
+        if (v < CV) {
+            unpack8(ld8(src + v * 8), f[j]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += f[j][e];
+        }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(C);
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int v = lane + j * 32;
+        if (v < CV) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = f[j][e] - mean;
+                ss += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
+    __half* dst = out + static_cast<long long>(row) * C;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int v = lane + j * 32;
+        if (v < CV) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                y[e] = (f[j][e] - mean) * rstd * __ldg(gamma + v * 8 + e) + __ldg(beta + v * 8 + e);
+            st8(dst + v * 8, pack8(y));
+        }
+    }
+}
+
+int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t st) {
+    if ((C % 8) || C > 2048) {
+        snprintf(g_kerr, sizeof(g_kerr), "layernorm: unsupported C=%d", C);
+        return -1;
+    }
+    if (rows <= 0) return 0;
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out);
+    return check_launch("layernorm");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// row softmax, in place
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long rows, int cols, int ld) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    __half* p = x + row * ld;
+    const bool vec = ((cols & 7) == 0) && ((ld & 7) == 0);
+    float m = -INFINITY;
+    if (vec) {
+        for (int v = lane; v < (cols >> 3); v += 32) {
+            float f[8];
+            unpack8(*reinterpret_cast<const Half8*>(p + v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m = fmaxf(m, f[e]);
+        }
+    } else {
+        for (int c = lane; c < cols; c += 32) m = fmaxf(m, __half2float(p[c]));
+    }
+    m = warp_max(m);
+    float s = 0.0f;
+    if (vec) {
+        for (int v = lane; v < (cols >> 3); v += 32) {
+            float f[8];
+            unpack8(*reinterpret_cast<const Half8*>(p + v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += __expf(f[e] - m);
+        }
+    } else {
+        for (int c = lane; c < cols; c += 32) s += __expf(__half2float(p[c]) - m);
+    }
+    const float inv = 1.0f / warp_sum(s);
+    if (vec) {
+        for (int v = lane; v < (cols >> 3); v += 32) {
+            float f[8];
+            unpack8(*reinterpret_cast<const Half8*>(p + v * 8), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __expf(f[e] - m) * inv;
+            st8(p + v * 8, pack8(f));
+        }
+    } else {
+        for (int c = lane; c < cols; c += 32) p[c] = __float2half_rn(__expf(__half2float(p[c]) - m) * inv);
+    }
+}
+
+int launch_softmax_rows(__half* x, long long rows, int cols, int ld, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, rows, cols, ld);
+    return check_launch("softmax_rows");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// attention with nkv <= 64 keys resident in shared memory
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ATTN_ROWS_PER_BLOCK = 32;
+// grid (ceil(nq / 32), heads, batch); block 128
+__global__ void __launch_bounds__(128)
+    attn_small_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, int ldk,
+                      const __half* __restrict__ v, int ldv, __half* __restrict__ out, int ldo, int nq, int nkv, int d,
+                      long long q_bs, long long kv_bs, long long o_bs, const int* __restrict__ kv_index, float scale,
+                      int kpitch) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* Ks = reinterpret_cast<__half*>(sm_raw);  // [nkv][kpitch]
+    __half* Vs = Ks + nkv * kpitch;                   // [nkv][d]
+    float* qs = reinterpret_cast<float*>(Vs + ((nkv * d + 7) & ~7));  // [4][d]
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int kvb = kv_index ? kv_index[b] : b;
+    const __half* kb = k + kvb * kv_bs + h * d;
+    const __half* vb = v + kvb * kv_bs + h * d;
+    for (int i = threadIdx.x; i < nkv * (d >> 1); i += blockDim.x) {
+        const int j = i / (d >> 1), c2 = i - j * (d >> 1);
+        reinterpret_cast<__half2*>(Ks + j * kpitch)[c2] =
+            __ldg(reinterpret_cast<const __half2*>(kb + static_cast<long long>(j) * ldk) + c2);
+        reinterpret_cast<__half2*>(Vs + j * d)[c2] =
+            __ldg(reinterpret_cast<const __half2*>(vb + static_cast<long long>(j) * ldv) + c2);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* qw = qs + warp * d;
+    const int row_end = min(nq, (blockIdx.x + 1) * ATTN_ROWS_PER_BLOCK);
+    for (int row = blockIdx.x * ATTN_ROWS_PER_BLOCK + warp; row < row_end; row += 4) {
+        const __half* qr = q + b * q_bs + static_cast<long long>(row) * ldq + h * d;
+        __syncwarp();
+        for (int c = lane; c < d; c += 32) qw[c] = __half2float(qr[c]) * scale;
+        __syncwarp();
+        float s0 = -INFINITY, s1 = -INFINITY;
+        if (lane < nkv) {
+            float a = 0.0f;
+            const __half2* kr = reinterpret_cast<const __half2*>(Ks + lane * kpitch);
+            for (int c2 = 0; c2 < (d >> 1); ++c2) {
+                const float2 t = __half22float2(kr[c2]);
+                a += qw[2 * c2] * t.x + qw[2 * c2 + 1] * t.y;
+            }
+            s0 = a;
+        }
+        if (lane + 32 < nkv) {
+            float a = 0.0f;
+            const __half2* kr = reinterpret_cast<const __half2*>(Ks + (lane + 32) * kpitch);
+            for (int c2 = 0; c2 < (d >> 1); ++c2) {
+                const float2 t = __half22float2(kr[c2]);
+                a += qw[2 * c2] * t.x + qw[2 * c2 + 1] * t.y;
+            }
+            s1 = a;
+        }
+        const float m = warp_max(fmaxf(s0, s1));
+        const float e0 = (lane < nkv) ? __expf(s0 - m) : 0.0f;
+        const float e1 = (lane + 32 < nkv) ? __expf(s1 - m) : 0.0f;
+        const float inv = 1.0f / warp_sum(e0 + e1);
+        const float p0 = e0 * inv, p1 = e1 * inv;
+        __half* orow = out + b * o_bs + static_cast<long long>(row) * ldo + h * d;
+        for (int c0 = 0; c0 < d; c0 += 32) {
+            const int c = c0 + lane;
+            float acc = 0.0f;
+            for (int j = 0; j < nkv; ++j) {
+                const float pj = __shfl_sync(0xffffffffu, (j < 32) ? p0 : p1, j & 31);
+                if (c < d) acc += pj * __half2float(Vs[j * d + c]);
+            }
+            if (c < d) orow[c] = __float2half_rn(acc);
+        }
+    }
+}
+
+int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out, int ldo,
+                      int nq, int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
+                      const int* kv_index, float scale, cudaStream_t st) {
+    if (nkv > 64 || nkv < 1 || (d & 1) || (ldk & 1) || (ldv & 1)) {
+        snprintf(g_kerr, sizeof(g_kerr), "attn_small: unsupported nkv=%d d=%d", nkv, d);
+        return -1;
+    }
+    const int kpitch = d + ((((d >> 1) & 1) == 0) ? 2 : 0);
+    const size_t smem = static_cast<size_t>(nkv) * kpitch * 2 + ((static_cast<size_t>(nkv) * d + 7) & ~size_t(7)) * 2 +
+                        4 * static_cast<size_t>(d) * 4;
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess) {
+            snprintf(g_kerr, sizeof(g_kerr), "attn_small: smem %zu too large", smem);
+            return -1;
+        }
+        smem_set = smem;
+    }
+    dim3 grid((nq + ATTN_ROWS_PER_BLOCK - 1) / ATTN_ROWS_PER_BLOCK, heads, batch);
+    attn_small_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs, kv_bs, o_bs, kv_index,
+                                              scale, kpitch);
+    return check_launch("attn_small");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// resampling / gathers
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    upsample2x_kernel(const __half* __restrict__ x, int H, int W, int CV, long long total, __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cv = static_cast<int>(i % CV);
+    long long t = i / CV;
+    const int ox = static_cast<int>(t % (2 * W));
+    t /= (2 * W);
+    const int oy = static_cast<int>(t % (2 * H));
+    const long long n = t / (2 * H);
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(x) + ((n * H + (oy >> 1)) * W + (ox >> 1)) * CV + cv);
+    reinterpret_cast<uint4*>(out)[i] = val;
+}
+int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* out, cudaStream_t st) {
+    if (C % 8) {
+        snprintf(g_kerr, sizeof(g_kerr), "upsample2x: C=%d", C);
+        return -1;
+    }
+    const long long total = static_cast<long long>(Nimg) * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, H, W, C / 8, total, out);
+    return check_launch("upsample2x");
+}
+
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const __half* __restrict__ x, int H, int W, int CV, int pad_lo,
+                                                        int Ho, int Wo, long long total, __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int cv = static_cast<int>(i % CV);
+    long long t = i / CV;
+    const int tap = static_cast<int>(t % 9);
+    t /= 9;
+    const int ox = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oy = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const int iy = 2 * oy + tap / 3 - pad_lo, ix = 2 * ox + tap % 3 - pad_lo;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        val = __ldg(reinterpret_cast<const uint4*>(x) + ((n * H + iy) * W + ix) * CV + cv);
+    reinterpret_cast<uint4*>(out)[i] = val;
+}
+int launch_im2col_s2(const __half* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, __half* out,
+                     cudaStream_t st) {
+    if (C % 8) {
+        snprintf(g_kerr, sizeof(g_kerr), "im2col_s2: C=%d", C);
+        return -1;
+    }
+    const long long total = static_cast<long long>(Nimg) * Ho * Wo * 9 * (C / 8);
+    im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, H, W, C / 8, pad_lo, Ho, Wo, total,
+                                                                                out);
+    return check_launch("im2col_s2");
+}
+
+__global__ void __launch_bounds__(256) patchify32_kernel(const float* __restrict__ x, long long total,
+                                                         __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kk = static_cast<int>(i % 3072);
+    const long long t = i / 3072;
+    const int patch = static_cast<int>(t % 49);
+    const long long n = t / 49;
+    const int c = kk >> 10, dy = (kk >> 5) & 31, dx = kk & 31;
+    const int py = patch / 7, px = patch - py * 7;
+    out[i] = __float2half_rn(__ldg(x + ((n * 3 + c) * 224 + py * 32 + dy) * 224 + px * 32 + dx));
+}
+int launch_patchify32(const float* x, int Nimg, __half* out, cudaStream_t st) {
+    const long long total = static_cast<long long>(Nimg) * 49 * 3072;
+    patchify32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, total, out);
+    return check_launch("patchify32");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// guidance + DDIM step (fp32, IEEE operation order of the reference; no fused multiply-add)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    guidance_ddim_kernel(const float* __restrict__ eps3, const float* __restrict__ lat, float* __restrict__ out,
+                         long long n, float cfg, float tg, float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev,
+                         float sqrt_beta_prev) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float eu = eps3[i], ec = eps3[n + i], et = eps3[2 * n + i];
+    // eps = eu + cfg*(ec-eu) + tg*(et-ec)        (stable_diffusion_pipeline.py:449-451)
+    float e = __fadd_rn(eu, __fmul_rn(cfg, __fsub_rn(ec, eu)));
+    e = __fadd_rn(e, __fmul_rn(tg, __fsub_rn(et, ec)));
+    // x0 = (x - sqrt(1-a_t) e) / sqrt(a_t);  x' = sqrt(a_prev) x0 + sqrt(1-a_prev) e     (utilities.py:477-505)
+    const float x0 = __fdiv_rn(__fsub_rn(lat[i], __fmul_rn(sqrt_beta_t, e)), sqrt_alpha_t);
+    out[i] = __fadd_rn(__fmul_rn(sqrt_alpha_prev, x0), __fmul_rn(sqrt_beta_prev, e));
+}
+int launch_guidance_ddim(const float* eps3, const float* latents_in, float* latents_out, int B, int chw, float cfg,
+                         float tg, float alpha_t, float alpha_prev, cudaStream_t st) {
+    const long long n = static_cast<long long>(B) * chw;
+    const float beta_t = 1.0f - alpha_t;
+    const float beta_prev = 1.0f - alpha_prev;  // (1 - a_prev - std_dev^2) with eta = 0
+    guidance_ddim_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+        eps3, latents_in, latents_out, n, cfg, tg, sqrtf(beta_t), sqrtf(alpha_t), sqrtf(alpha_prev), sqrtf(beta_prev));
+    return check_launch("guidance_ddim");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layout packers
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    pack_unet_input_kernel(const float* __restrict__ lat, const float* __restrict__ mask3,
+                           const float* __restrict__ masked3, int B, int hw, __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (sample, pixel)
+    if (i >= static_cast<long long>(3) * B * hw) return;
+    const int s = static_cast<int>(i / hw), p = static_cast<int>(i % hw);
+    const int b = s % B;
+    __align__(16) __half h[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) h[c] = __float2half_rn(0.0f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) h[c] = __float2half_rn(lat[(static_cast<long long>(b) * 4 + c) * hw + p]);
+    h[4] = __float2half_rn(mask3[static_cast<long long>(s) * hw + p]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) h[5 + c] = __float2half_rn(masked3[(static_cast<long long>(s) * 4 + c) * hw + p]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = reinterpret_cast<const uint4*>(h)[j];
+}
+int launch_pack_unet_input(const float* latents, const float* mask3, const float* masked3, int B, int hw, __half* out,
+                           cudaStream_t st) {
+    const long long n = static_cast<long long>(3) * B * hw;
+    pack_unet_input_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(latents, mask3, masked3, B, hw, out);
+    return check_launch("pack_unet_input");
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int HW, int Cpad,
+                                                               float divisor, long long total,
+                                                               __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (n, pixel, cpad/8)
+    if (i >= total) return;
+    const int CV = Cpad >> 3;
+    const int cv = static_cast<int>(i % CV);
+    const long long t = i / CV;
+    const int p = static_cast<int>(t % HW);
+    const long long n = t / HW;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = cv * 8 + e;
+        f[e] = (c < C) ? __fdiv_rn(__ldg(x + (n * C + c) * HW + p), divisor) : 0.0f;
+    }
+    st8(out + i * 8, pack8(f));
+}
+int launch_nchw_to_nhwc_pad(const float* x, int Nimg, int C, int HW, int Cpad, float divisor, __half* out,
+                            cudaStream_t st) {
+    const long long total = static_cast<long long>(Nimg) * HW * (Cpad / 8);
+    nchw_to_nhwc_pad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, HW, Cpad, divisor, total,
+                                                                                       out);
+    return check_launch("nchw_to_nhwc_pad");
+}
+
+__global__ void __launch_bounds__(256) vae_sample_kernel(const float* __restrict__ mom, const float* __restrict__ noise,
+                                                         int hw, long long total, float scale, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, c<4, p)
+    if (i >= total) return;
+    const int p = static_cast<int>(i % hw);
+    const long long t = i / hw;
+    const int c = static_cast<int>(t % 4);
+    const long long b = t / 4;
+    const float mean = mom[(b * 8 + c) * hw + p];
+    float z = mean;
+    if (noise != nullptr) {
+        float logvar = mom[(b * 8 + 4 + c) * hw + p];
+        logvar = fminf(fmaxf(logvar, -30.0f), 20.0f);
+        z = __fadd_rn(mean, __fmul_rn(expf(0.5f * logvar), noise[i]));
+    }
+    out[i] = __fmul_rn(scale, z);
+}
+int launch_vae_sample(const float* moments, const float* noise, int B, int hw, float scale, float* out,
+                      cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * 4 * hw;
+    vae_sample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(moments, noise, hw, total, scale, out);
+    return check_launch("vae_sample");
+}
+
+__global__ void __launch_bounds__(256) mask_nearest_kernel(const float* __restrict__ in, int R, int f, long long total,
+                                                           float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = R / f;
+    const int x = static_cast<int>(i % r);
+    const long long t = i / r;
+    const int y = static_cast<int>(t % r);
+    const long long b = t / r;
+    out[i] = in[(b * R + static_cast<long long>(y) * f) * R + static_cast<long long>(x) * f];
+}
+int launch_mask_nearest(const float* in, int B, int R, int f, float* out, cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * (R / f) * (R / f);
+    mask_nearest_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, R, f, total, out);
+    return check_launch("mask_nearest");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// canvas pre-process (K19) and post-process (K18)
+// ------------------------------------------------------------------------------------------------------------
+// pass 1: row-wise running max of alpha over x in [x - pad/2, x + pad - pad/2 - 1]
+__global__ void __launch_bounds__(256) dilate_rows_kernel(const float* __restrict__ canvas, int R, int pad,
+                                                          long long total, float* __restrict__ scratch) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
+    if (i >= total) return;
+    const int x = static_cast<int>(i % R);
+    const long long t = i / R;
+    const int y = static_cast<int>(t % R);
+    const long long b = t / R;
+    const float* a = canvas + ((b * 4 + 3) * R + y) * R;
+    const int lo = max(0, x - pad / 2), hi = min(R - 1, x + pad - pad / 2 - 1);
+    float m = -1e4f;
+    for (int xx = lo; xx <= hi; ++xx) m = fmaxf(m, __ldg(a + xx));
+    scratch[i] = m;
+}
+__global__ void __launch_bounds__(256)
+    canvas_finish_kernel(const float* __restrict__ canvas, const float* __restrict__ brush,
+                         const float* __restrict__ scratch, int R, int pad, long long total,
+                         float* __restrict__ masked_img, float* __restrict__ mask, float* __restrict__ ctx_img,
+                         float* __restrict__ ctx_mask) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
+    if (i >= total) return;
+    const int x = static_cast<int>(i % R);
+    const long long t = i / R;
+    const int y = static_cast<int>(t % R);
+    const long long b = t / R;
+    const long long plane = static_cast<long long>(R) * R;
+    const int lo = max(0, y - pad / 2), hi = min(R - 1, y + pad - pad / 2 - 1);
+    float dil = -1e4f;
+    for (int yy = lo; yy <= hi; ++yy) dil = fmaxf(dil, __ldg(scratch + (b * R + yy) * R + x));
+    const float alpha = canvas[(b * 4 + 3) * plane + static_cast<long long>(y) * R + x];
+    const float hint = __fsub_rn(1.0f, dil);
+    const long long pix = static_cast<long long>(y) * R + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float img = __fsub_rn(__fmul_rn(canvas[(b * 4 + c) * plane + pix], 2.0f), 1.0f);
+        const float mi = __fmul_rn(img, alpha);
+        const float bs = __fsub_rn(__fmul_rn(__ldg(brush + c * plane + pix), 2.0f), 1.0f);
+        masked_img[(b * 3 + c) * plane + pix] = mi;
+        ctx_img[(b * 3 + c) * plane + pix] = __fadd_rn(mi, __fmul_rn(bs, hint));
+    }
+    mask[b * plane + pix] = __fsub_rn(1.0f, alpha);
+    const float cm = fminf(fmaxf(__fadd_rn(alpha, hint), 0.0f), 1.0f);
+    ctx_mask[b * plane + pix] = __fsub_rn(1.0f, cm);
+}
+int launch_canvas_preprocess(const float* canvas, const float* brush, int B, int R, int pad, float* masked_img,
+                             float* mask, float* ctx_img, float* ctx_mask, float* scratch, cudaStream_t st) {
+    if (pad < 1) pad = 1;
+    const long long total = static_cast<long long>(B) * R * R;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    dilate_rows_kernel<<<blocks, 256, 0, st>>>(canvas, R, pad, total, scratch);
+    if (check_launch("dilate_rows")) return -1;
+    canvas_finish_kernel<<<blocks, 256, 0, st>>>(canvas, brush, scratch, R, pad, total, masked_img, mask, ctx_img,
+                                                ctx_mask);
+    return check_launch("canvas_finish");
+}
+
+__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ canvas, const float* __restrict__ raw,
+                                                        int R, long long total, float* __restrict__ out_f32,
+                                                        unsigned char* __restrict__ out_u8) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, pix)
+    if (i >= total) return;
+    const long long plane = static_cast<long long>(R) * R;
+    const long long pix = i % plane, b = i / plane;
+    const float alpha = canvas[(b * 4 + 3) * plane + pix];
+    const float ia = __fsub_rn(1.0f, alpha);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = __fadd_rn(__fmul_rn(canvas[(b * 4 + c) * plane + pix], alpha),
+                                  __fmul_rn(raw[(b * 3 + c) * plane + pix], ia));
+        if (out_f32) out_f32[(b * 3 + c) * plane + pix] = v;
+        if (out_u8) out_u8[(b * plane + pix) * 3 + c] = static_cast<unsigned char>(__fmul_rn(v, 255.0f));
+    }
+}
+int launch_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
+                     cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * R * R;
+    composite_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(canvas, raw, R, total, out_f32,
+                                                                                out_u8hwc);
+    return check_launch("composite");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_rows_bcast_kernel(__half* __restrict__ x, const float* __restrict__ add,
+                                                             long long total, int C, int period) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    x[i] = __float2half_rn(__half2float(x[i]) + add[(r % period) * C + c]);
+}
+int launch_add_rows_bcast(__half* x, const float* add, long long rows, int C, int period, cudaStream_t st) {
+    const long long total = rows * C;
+    add_rows_bcast_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, add, total, C, period);
+    return check_launch("add_rows_bcast");
+}
+__global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ out,
+                                                         long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2half_rn(x[i]);
+}
+int launch_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    f32_to_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, out, n);
+    return check_launch("f32_to_f16");
+}
+__global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ out,
+                                                         long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __half2float(x[i]);
+}
+int launch_f16_to_f32(const __half* x, float* out, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    f16_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, out, n);
+    return check_launch("f16_to_f32");
+}
+__global__ void __launch_bounds__(256) copy_f32_kernel(const float* __restrict__ s, float* __restrict__ d, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = s[i];
+}
+int launch_copy_f32(const float* src, float* dst, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    copy_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    return check_launch("copy_f32");
+}
+
+// diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): emb = [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / (dim/2))
+__global__ void timestep_embedding_kernel(const float* __restrict__ ts, int n, int dim, __half* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    const int r = i / dim, c = i % dim;
+    const int half_dim = dim / 2;
+    const int k = c % half_dim;
+    const float f = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half_dim));
+    const float a = ts[r] * f;
+    out[i] = __float2half_rn(c < half_dim ? cosf(a) : sinf(a));
+}
+int launch_timestep_embedding(const float* timesteps, int n, int dim, __half* out, cudaStream_t st) {
+    timestep_embedding_kernel<<<(n * dim + 255) / 256, 256, 0, st>>>(timesteps, n, dim, out);
+    return check_launch("timestep_embedding");
+}
+
+// CLIP token assembly: out[n, 0, :] = cls + pos[0]; out[n, 1+j, :] = patch_tok[n*49+j] + pos[1+j]
+__global__ void __launch_bounds__(256) clip_embed_kernel(const __half* __restrict__ tok, const float* __restrict__ cls,
+                                                         const float* __restrict__ pos, int C, long long total,
+                                                         __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    const int t = static_cast<int>(r % 50);
+    const long long n = r / 50;
+    const float base = (t == 0) ? cls[c] : __half2float(tok[(n * 49 + (t - 1)) * C + c]);
+    out[i] = __float2half_rn(base + pos[t * C + c]);
+}
+int launch_clip_embed(const __half* patch_tok, const float* cls, const float* pos, int Nimg, int C, __half* out,
+                      cudaStream_t st) {
+    const long long total = static_cast<long long>(Nimg) * 50 * C;
+    clip_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(patch_tok, cls, pos, C, total, out);
+    return check_launch("clip_embed");
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __half* __restrict__ x, int ld,
+                                                          const int* __restrict__ idx, int C, long long total,
+                                                          __half* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    const long long r = i / C;
+    out[i] = x[static_cast<long long>(idx[r]) * ld + c];
+}
+int launch_gather_rows(const __half* x, int ld, const int* rows_idx, int nrows, int C, __half* out, cudaStream_t st) {
+    const long long total = static_cast<long long>(nrows) * C;
+    gather_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, ld, rows_idx, C, total, out);
+    return check_launch("gather_rows");
+}
+
+}  // namespace dtp

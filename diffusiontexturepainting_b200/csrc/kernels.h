@@ -1,0 +1,73 @@
+// HBM-bound kernels of the stamp path (norms, softmax, small attention, resampling, scheduler step, canvas pre/post).
+// Activations are NHWC fp16 (rows = pixels, row length = channels); latents / images at the boundary are NCHW fp32
+// exactly as the reference façade hands them over (trt_inference/inpaint_pipeline.py:52-153).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace dtp {
+
+const char* kernels_last_error();
+
+// GroupNorm (+SiLU) over one or two NHWC sources (channel concat, never materialised before the norm).
+// stats_ws: float[Nimg * chunks * groups * 2 + Nimg * groups * 2]
+int gn_num_chunks(int HW, int C);
+size_t gn_ws_floats(int Nimg, int HW, int C, int groups);
+int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
+                     const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
+                     cudaStream_t st);
+
+int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
+                     cudaStream_t st);
+// in-place row softmax (fp32 math) over fp16 rows
+int launch_softmax_rows(__half* x, long long rows, int cols, int ld, cudaStream_t st);
+
+// attention with a short key/value sequence (nkv <= 64) held in shared memory: cross-attention on the 14 image tokens,
+// CLIP (50 tokens), patch towers (1/4/9 tokens) and UNet self-attention at <= 8x8 latents.
+// q: [batch][nq][ldq] with head h at columns h*d..; k/v: [kvbatch][nkv][ld*]; kv_index (device, nullable) maps batch ->
+// kvbatch.
+int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out, int ldo,
+                      int nq, int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
+                      const int* kv_index, float scale, cudaStream_t st);
+
+int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* out, cudaStream_t st);
+// stride-2 3x3 gather: out[(n,oy,ox)][tap*C + c] = x[n, 2*oy+ky-pad_lo, 2*ox+kx-pad_lo, c] (0 outside)
+int launch_im2col_s2(const __half* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, __half* out,
+                     cudaStream_t st);
+// stride-32 32x32 patch gather for the CLIP patch embedding: x fp32 [N,3,224,224] -> fp16 [N*49, 3072] (k = c*1024+dy*32+dx)
+int launch_patchify32(const float* x, int Nimg, __half* out, cudaStream_t st);
+
+// eps3: (3B, chw) fp32 = [uncond | cond | texture-guidance]; DDIM eta=0 epsilon-prediction step
+// (stable_diffusion_pipeline.py:449-455, utilities.py:441-522)
+int launch_guidance_ddim(const float* eps3, const float* latents_in, float* latents_out, int B, int chw, float cfg,
+                         float tg, float alpha_t, float alpha_prev, cudaStream_t st);
+// (3B, hw, 64) fp16 NHWC <- [latents(4) | mask(1) | masked latents(4) | zero pad] (stable_diffusion_pipeline.py:423-427)
+int launch_pack_unet_input(const float* latents, const float* mask3, const float* masked3, int B, int hw, __half* out,
+                           cudaStream_t st);
+// fp32 NCHW -> fp16 NHWC with channel padding; out = x / divisor
+int launch_nchw_to_nhwc_pad(const float* x, int Nimg, int C, int HW, int Cpad, float divisor, __half* out,
+                            cudaStream_t st);
+// latent = 0.18215 * (mean + exp(0.5*clamp(logvar,-30,20)) * noise); moments fp32 NCHW (B,8,hw); noise nullable
+int launch_vae_sample(const float* moments, const float* noise, int B, int hw, float scale, float* out, cudaStream_t st);
+// nearest downsample of an fp32 (B,1,R,R) mask to (B,1,R/f,R/f): out[i,j] = in[f*i, f*j] (inpaint_pipeline.py:114-115)
+int launch_mask_nearest(const float* in, int B, int R, int f, float* out, cudaStream_t st);
+
+// K19: trt_model.py:103-109 + handler.py:25-33. scratch: float[B*R*R]
+int launch_canvas_preprocess(const float* canvas, const float* brush, int B, int R, int pad, float* masked_img,
+                             float* mask, float* ctx_img, float* ctx_mask, float* scratch, cudaStream_t st);
+// K18: model_base.py:56-58 (+ handler.py:55-56 when out_u8hwc != null)
+int launch_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
+                     cudaStream_t st);
+
+// misc small helpers used by the runtime
+int launch_add_rows_bcast(__half* x, const float* add, long long rows, int C, int period, cudaStream_t st);  // x[r,:] += add[r % period,:]
+int launch_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t st);
+int launch_f16_to_f32(const __half* x, float* out, long long n, cudaStream_t st);
+int launch_timestep_embedding(const float* timesteps, int n, int dim, __half* out, cudaStream_t st);
+int launch_copy_f32(const float* src, float* dst, long long n, cudaStream_t st);
+// out[r, :] = concat rows: CLIP class token + patch tokens + positional embedding
+int launch_clip_embed(const __half* patch_tok, const float* cls, const float* pos, int Nimg, int C, __half* out,
+                      cudaStream_t st);
+int launch_gather_rows(const __half* x, int ld, const int* rows_idx, int nrows, int C, __half* out, cudaStream_t st);
+
+}  // namespace dtp

@@ -1,0 +1,96 @@
+/*
+ * dtp.h — C-ABI of libdtp_sm100.so: the sm_100a brush-stamp inpainting path of Diffusion Texture Painting.
+ *
+ * This is the boundary a maintainer of nv-tlabs/DiffusionTexturePainting binds (ctypes from Python; see
+ * INTEGRATION.md) in place of the TensorRT engine layer of trt_inference/:
+ *
+ *   reference interface (file:line, relative to the reference repo)             entry point here
+ *   -------------------------------------------------------------------------   --------------------------------
+ *   Engine.load/activate/allocate_buffers   trt_inference/utilities.py:221-250   dtp_create, dtp_set_tensor,
+ *   StableDiffusionPipeline.loadEngines     stable_diffusion_pipeline.py:189-334   dtp_finalize_weights
+ *   UNet.get_model LoRA merge               trt_inference/models.py:1042-1093     (host side, weights.py) -> dtp_set_tensor
+ *   ConditionPatchEncoder.forward           trt_inference/image_encoder.py:78-98  dtp_encode_patches
+ *   text_embeddings = cat([neg,prompt,prompt]) inpaint_pipeline.py:140            dtp_set_condition
+ *   InpaintPipeline.update_infer_settings   inpaint_pipeline.py:39-50             dtp_set_schedule
+ *   InpaintPipeline.infer                   inpaint_pipeline.py:52-153            dtp_infer
+ *   TRTConditionalInpainter.generate_raw    trt_inference/trt_model.py:90-121     dtp_stamp (pre-process + infer [+ composite])
+ *   encode_image -> Engine.infer('vae_encoder')  stable_diffusion_pipeline.py:464-474   dtp_vae_encode
+ *   Engine.infer('unet')                    stable_diffusion_pipeline.py:436-441  dtp_unet_forward
+ *   scheduler.step + guidance               stable_diffusion_pipeline.py:449-455, utilities.py:441-522   dtp_op_ddim_step
+ *   decode_latent -> Engine.infer('vae')    stable_diffusion_pipeline.py:476-484  dtp_vae_decode
+ *   add_extra_context (kornia dilation)     trt_inference/handler.py:25-33        dtp_op_canvas_preprocess
+ *   ConditionalInpainterBase.generate       trt_inference/model_base.py:51-58     dtp_op_composite
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure (never throws across the ABI);
+ * dtp_last_error()/dtp_ops_last_error() return a human-readable reason. All pointers are BORROWED DEVICE pointers
+ * unless the name says "host"; they must stay valid until the stream reaches the end of the call. Work is enqueued
+ * on the caller's stream (pass torch.cuda.current_stream().cuda_stream); no hidden synchronisation unless stated.
+ * A handle is bound to the CUDA device current at dtp_create and is not thread-safe (one handle per GPU / process).
+ * "f16" buffers are IEEE binary16; activations are NHWC (rows = pixels, row length = channels).
+ */
+#ifndef DTP_H_
+#define DTP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * epilogue flags of the contraction entry points (same values as dtp::GemmFlags)
+ * ---------------------------------------------------------------------------------------------------------- */
+#define DTP_EPI_GELU (1 << 0)
+#define DTP_EPI_QUICKGELU (1 << 1)
+#define DTP_EPI_SILU (1 << 2)
+#define DTP_EPI_GEGLU (1 << 3)
+#define DTP_EPI_BIAS_M (1 << 4)
+#define DTP_EPI_OUT_F32_NCHW (1 << 5)
+#define DTP_EPI_IMG01 (1 << 6)
+#define DTP_EPI_OUT_F32 (1 << 7)
+
+/* ------------------------------------------------------------------------------------------------------------
+ * operator entry points (one kernel family per call; parity tests and roofline isolation)
+ * ---------------------------------------------------------------------------------------------------------- */
+const char* dtp_ops_last_error(void);
+
+/* out[M,N] = epilogue(alpha * [A0 | A1][M,K0+K1] * Wt[N,K0+K1]^T + bias) (+ residual). BN<=0: pick tile/split. */
+int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, int K1, int M, const void* Wt, int ldw,
+                  int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
+                  int hw_out, int BN, int splits, void* stream);
+/* 3x3 stride-1 pad-1 conv over NHWC sources (Nimg,H,W,C0) [| (Nimg,H,W,C1)]; Wt [Cout, 9*(C0+C1)], k = tap*C + c */
+int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int H, int W, const void* Wt, int Cout,
+                   const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
+                   int hw_out, int BN, int splits, void* stream);
+/* batched D_z = alpha * A_z * B_z^T over z = (z1 < nz1, z2 < nz2); b_mn: B_z given as [K,N] row-major */
+int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
+               long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
+               long long out_zs2, float alpha, int flags, int BN, void* stream);
+int dtp_op_groupnorm(const void* x0, int C0, const void* x1, int C1, int Nimg, int HW, int groups, const float* gamma,
+                     const float* beta, float eps, int silu, void* out, void* stream);
+int dtp_op_layernorm(const void* x, int rows, int C, const float* gamma, const float* beta, float eps, void* out,
+                     void* stream);
+int dtp_op_softmax(void* x, long long rows, int cols, int ld, void* stream);
+int dtp_op_attn_small(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int nq,
+                      int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
+                      const int* kv_index, float scale, void* stream);
+int dtp_op_upsample2x(const void* x, int Nimg, int H, int W, int C, void* out, void* stream);
+int dtp_op_im2col_s2(const void* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, void* out, void* stream);
+/* eps3 (3B,chw) f32 [uncond|cond|tg]; DDIM eta=0 step with the reference's operation order */
+int dtp_op_ddim_step(const float* eps3, const float* latents_in, float* latents_out, int B, int chw, float cfg, float tg,
+                     float alpha_t, float alpha_prev, void* stream);
+int dtp_op_pack_unet_input(const float* latents, const float* mask3, const float* masked3, int B, int hw, void* out,
+                           void* stream);
+int dtp_op_nchw_to_nhwc_pad(const float* x, int Nimg, int C, int HW, int Cpad, float divisor, void* out, void* stream);
+/* canvas (B,4,R,R) f32 0..1, brush (1,3,R,R) f32 0..1 -> masked image, mask (1 = generate), context pair. scratch: B*R*R floats */
+int dtp_op_canvas_preprocess(const float* canvas, const float* brush, int B, int R, int pad, float* masked_img,
+                             float* mask, float* ctx_img, float* ctx_mask, float* scratch, void* stream);
+/* rgb*alpha + raw*(1-alpha); optional uint8 HWC copy (truncating x255 as handler.py:55-56) */
+int dtp_op_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTP_H_ */
