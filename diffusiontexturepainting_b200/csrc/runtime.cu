@@ -1,0 +1,1545 @@
+// Native runtime of the stamp path. See runtime.h.
+#include "runtime.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace dtp {
+
+// ------------------------------------------------------------------------------------------------------------
+// Arena
+// ------------------------------------------------------------------------------------------------------------
+void* Arena::alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    if (bytes == 0) bytes = 1024;
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+        if (it->second >= bytes) {
+            const size_t off = it->first, sz = it->second;
+            free_.erase(it);
+            if (sz > bytes) free_[off + bytes] = sz - bytes;
+            live_[off] = bytes;
+            used_ += bytes;
+            peak_ = std::max(peak_, off + bytes);
+            return base_ + off;
+        }
+    }
+    return nullptr;
+}
+
+void Arena::release(void* p) {
+    if (!p) return;
+    const size_t off = static_cast<size_t>(static_cast<char*>(p) - base_);
+    auto it = live_.find(off);
+    if (it == live_.end()) return;
+    size_t sz = it->second;
+    live_.erase(it);
+    used_ -= sz;
+    size_t start = off;
+    auto nx = free_.lower_bound(off);
+    if (nx != free_.end() && nx->first == off + sz) {
+        sz += nx->second;
+        nx = free_.erase(nx);
+    }
+    if (nx != free_.begin()) {
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == off) {
+            start = pv->first;
+            sz += pv->second;
+            free_.erase(pv);
+        }
+    }
+    free_[start] = sz;
+}
+
+int Plan::run(cudaStream_t st, long long* launch_counter) const {
+    for (const auto& op : ops) {
+        const int r = op(st);
+        if (r < 0) return r;
+        if (launch_counter) *launch_counter += r;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Builder: appends launch closures to a plan, carving activations from the arena
+// ------------------------------------------------------------------------------------------------------------
+struct Lin {
+    const __half* A0 = nullptr;
+    int lda0 = 0, K0 = 0;
+    const __half* A1 = nullptr;
+    int lda1 = 0, K1 = 0;
+    long long M = 0;
+    const __half* W = nullptr;
+    int ldw = 0, N = 0;
+    const float* bias = nullptr;
+    const __half* res = nullptr;
+    int ldr = 0;
+    void* out = nullptr;
+    int ldc = 0;
+    int flags = 0;
+    float alpha = 1.0f;
+    int hw_out = 0;
+};
+
+struct Builder {
+    Engine& e;
+    Plan& plan;
+    std::string prefix;
+    bool ok = true;
+
+    Builder(Engine& eng, Plan& p, const std::string& pre) : e(eng), plan(p), prefix(pre) {}
+
+    void fail(const std::string& m) {
+        if (ok) e.err_ = m;
+        ok = false;
+    }
+    const WT* wt(const std::string& name) {
+        const WT* t = e.find(prefix + name);
+        if (!t) fail("missing weight tensor '" + prefix + name + "'");
+        return t;
+    }
+    const __half* W16(const std::string& name, int* rows = nullptr, int* cols = nullptr) {
+        const WT* t = wt(name);
+        if (!t) return nullptr;
+        if (t->dtype != 1 || t->shape.size() != 2) {
+            fail("weight '" + prefix + name + "' must be a 2-D f16 matrix");
+            return nullptr;
+        }
+        if (rows) *rows = static_cast<int>(t->shape[0]);
+        if (cols) *cols = static_cast<int>(t->shape[1]);
+        return static_cast<const __half*>(t->dev);
+    }
+    const float* F32(const std::string& name) {
+        const WT* t = wt(name);
+        if (!t) return nullptr;
+        if (t->dtype != 0) {
+            fail("weight '" + prefix + name + "' must be f32");
+            return nullptr;
+        }
+        return static_cast<const float*>(t->dev);
+    }
+    Act alloc(int N, int H, int W, int C) {
+        Act a;
+        a.N = N;
+        a.H = H;
+        a.W = W;
+        a.C = C;
+        a.p = static_cast<__half*>(e.arena_.alloc(a.bytes()));
+        if (!a.p) {
+            char buf[160];
+            snprintf(buf, sizeof(buf), "activation arena exhausted (need %zu more bytes, capacity %zu): raise arena_bytes",
+                     a.bytes(), e.arena_.capacity());
+            fail(buf);
+        }
+        return a;
+    }
+    Act like(const Act& a, int C) { return alloc(a.N, a.H, a.W, C); }
+    void* raw(size_t bytes) {
+        void* p = e.arena_.alloc(bytes);
+        if (!p) fail("activation arena exhausted: raise arena_bytes");
+        return p;
+    }
+    void release(Act& a) {
+        e.arena_.release(a.p);
+        a.p = nullptr;
+    }
+    void release_raw(void* p) { e.arena_.release(p); }
+
+    void push_gemm(GemmOp op) {
+        e.ws_needed_ = std::max(e.ws_needed_, gemm_workspace_bytes(&op));
+        Engine* eng = &e;
+        plan.ops.push_back([op, eng](cudaStream_t st) mutable -> int {
+            op.p.workspace = eng->ws_;
+            if (gemm_launch(&op, st)) {
+                eng->err_ = std::string("contraction launch failed: ") + gemm_last_error();
+                return -1;
+            }
+            return op.p.splits > 1 ? 2 : 1;
+        });
+    }
+
+    void linear(const Lin& a) {
+        if (!ok) return;
+        GemmOp op;
+        int BN, splits;
+        const int kb = (a.K0 + 63) / 64 + (a.A1 ? (a.K1 + 63) / 64 : 0);
+        gemm_pick_config(static_cast<int>((a.M + 127) / 128), a.N, kb, a.flags, &BN, &splits);
+        if (gemm_setup_linear(&op, a.A0, a.lda0, a.K0, a.A1, a.lda1, a.K1, static_cast<int>(a.M), a.W, a.ldw, a.N, BN,
+                              splits)) {
+            fail(std::string("linear setup: ") + gemm_last_error());
+            return;
+        }
+        op.p.bias = a.bias;
+        op.p.residual = a.res;
+        op.p.ldr = a.ldr;
+        op.p.out = a.out;
+        op.p.ldc = a.ldc > 0 ? a.ldc : a.N;
+        op.p.flags |= a.flags;
+        op.p.alpha = a.alpha;
+        op.p.hw_out = a.hw_out;
+        push_gemm(op);
+    }
+
+    // 3x3 stride-1 pad-1 conv over one or two NHWC sources; w_name: [Cout, 9*(C0+C1)] f16
+    void conv3x3_into(const Act& a0, const Act& a1, const std::string& w_name, const float* bias, const __half* res,
+                      int ldr, void* out, int ldc, int flags, int hw_out) {
+        if (!ok) return;
+        int cout = 0, kk = 0;
+        const __half* W = W16(w_name, &cout, &kk);
+        if (!W) return;
+        const int C = a0.C + (a1.p ? a1.C : 0);
+        if (kk != 9 * C) {
+            fail("conv weight '" + prefix + w_name + "' has K=" + std::to_string(kk) + ", expected " +
+                 std::to_string(9 * C));
+            return;
+        }
+        GemmOp probe, op;
+        if (gemm_setup_conv3x3(&probe, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, 128, 1)) {
+            fail(std::string("conv setup: ") + gemm_last_error());
+            return;
+        }
+        int BN, splits;
+        gemm_pick_config(probe.grid_m, cout, probe.p.num_kb, flags, &BN, &splits);
+        if (gemm_setup_conv3x3(&op, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, BN, splits)) {
+            fail(std::string("conv setup: ") + gemm_last_error());
+            return;
+        }
+        op.p.bias = bias;
+        op.p.residual = res;
+        op.p.ldr = ldr;
+        op.p.out = out;
+        op.p.ldc = ldc > 0 ? ldc : cout;
+        op.p.flags |= flags;
+        op.p.hw_out = hw_out;
+        push_gemm(op);
+    }
+    Act conv3x3(const Act& a0, const Act& a1, const std::string& p, const float* bias_override, const __half* res) {
+        int cout = 0;
+        W16(p + ".weight", &cout, nullptr);
+        if (!ok) return Act{};
+        Act out = like(a0, cout);
+        if (!ok) return out;
+        conv3x3_into(a0, a1, p + ".weight", bias_override ? bias_override : F32(p + ".bias"), res, cout, out.p, cout, 0,
+                     0);
+        return out;
+    }
+
+    Act groupnorm(const Act& a0, const Act& a1, const std::string& p, float eps, int silu) {
+        if (!ok) return Act{};
+        const int C = a0.C + (a1.p ? a1.C : 0);
+        Act out = like(a0, C);
+        const int HW = a0.H * a0.W;
+        const int groups = e.cfg_.groups;
+        float* ws = static_cast<float*>(raw(gn_ws_floats(a0.N, HW, C, groups) * sizeof(float)));
+        const float* g = F32(p + ".weight");
+        const float* bt = F32(p + ".bias");
+        if (!ok) return out;
+        Engine* eng = &e;
+        const __half *x0 = a0.p, *x1 = a1.p;
+        const int C0 = a0.C, C1 = a1.p ? a1.C : 0, Nimg = a0.N;
+        __half* o = out.p;
+        plan.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_groupnorm(x0, C0, x1, C1, Nimg, HW, groups, g, bt, eps, silu, o, ws, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 3;
+        });
+        release_raw(ws);  // stream-ordered: the next consumer of this slab runs after the norm
+        return out;
+    }
+
+    void layernorm(const Act& x, const std::string& p, __half* out) {
+        if (!ok) return;
+        const float* g = F32(p + ".weight");
+        const float* bt = F32(p + ".bias");
+        if (!ok) return;
+        Engine* eng = &e;
+        const __half* xp = x.p;
+        const int rows = static_cast<int>(x.rows()), C = x.C;
+        plan.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_layernorm(xp, rows, C, g, bt, 1e-5f, out, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+    }
+
+    // q/k/v given as pointers with row strides; batch entries `seq` rows apart
+    void attention(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out, int ldo,
+                   int nq, int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
+                   const int* kv_index) {
+        if (!ok) return;
+        Engine* eng = &e;
+        const float scale = 1.0f / sqrtf(static_cast<float>(d));
+        if (nkv <= 64) {
+            plan.ops.push_back([=](cudaStream_t st) -> int {
+                if (launch_attn_small(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, heads, d, batch, q_bs, kv_bs, o_bs,
+                                      kv_index, scale, st)) {
+                    eng->err_ = kernels_last_error();
+                    return -1;
+                }
+                return 1;
+            });
+            return;
+        }
+        if (kv_index) {
+            fail("indexed key/value batches are only supported for short sequences");
+            return;
+        }
+        // scores = scale * Q K^T (fp16, materialised), row softmax, out = P V with V consumed MN-major
+        const long long srows = static_cast<long long>(batch) * heads * nq;
+        const int ldS = (nkv + 7) & ~7;
+        __half* S = static_cast<__half*>(raw(static_cast<size_t>(srows) * ldS * sizeof(__half)));
+        if (!ok) return;
+        GemmOp qk, pv;
+        int BN, sp;
+        const int mt = ((nq + 127) / 128) * heads * batch;
+        gemm_pick_config(mt, nkv, (d + 63) / 64, 0, &BN, &sp);
+        if (gemm_setup_batched(&qk, q, ldq, d, q_bs, k, ldk, d, kv_bs, 0, nq, nkv, d, heads, batch, BN)) {
+            fail(std::string("attention QK setup: ") + gemm_last_error());
+            return;
+        }
+        qk.p.out = S;
+        qk.p.ldc = ldS;
+        qk.p.out_zs1 = static_cast<long long>(nq) * ldS;
+        qk.p.out_zs2 = static_cast<long long>(heads) * nq * ldS;
+        qk.p.alpha = scale;
+        push_gemm(qk);
+        plan.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_softmax_rows(S, srows, nkv, ldS, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+        gemm_pick_config(mt, d, (nkv + 63) / 64, GEMM_B_MN, &BN, &sp);
+        if (gemm_setup_batched(&pv, S, ldS, static_cast<long long>(nq) * ldS, static_cast<long long>(heads) * nq * ldS,
+                               v, ldv, d, kv_bs, 1, nq, d, nkv, heads, batch, BN)) {
+            fail(std::string("attention PV setup: ") + gemm_last_error());
+            return;
+        }
+        pv.p.out = out;
+        pv.p.ldc = ldo;
+        pv.p.out_zs1 = d;
+        pv.p.out_zs2 = o_bs;
+        push_gemm(pv);
+        release_raw(S);
+    }
+
+    Act upsample2x(const Act& x) {
+        if (!ok) return Act{};
+        Act out = alloc(x.N, 2 * x.H, 2 * x.W, x.C);
+        if (!ok) return out;
+        Engine* eng = &e;
+        const __half* xp = x.p;
+        __half* o = out.p;
+        const int N = x.N, H = x.H, W = x.W, C = x.C;
+        plan.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_upsample2x(xp, N, H, W, C, o, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+        return out;
+    }
+
+    // stride-2 3x3 conv: gather + linear. pad_lo = 1 (UNet, symmetric pad 1) or 0 (VAE, F.pad (0,1,0,1))
+    Act downsample(const Act& x, const std::string& p, int pad_lo) {
+        if (!ok) return Act{};
+        const int Ho = x.H / 2, Wo = x.W / 2;
+        Act col = alloc(x.N, Ho, Wo, 9 * x.C);
+        int cout = 0, kk = 0;
+        const __half* W = W16(p + ".weight", &cout, &kk);
+        if (!ok) return Act{};
+        if (kk != 9 * x.C) {
+            fail("downsample weight '" + prefix + p + "' has unexpected K");
+            return Act{};
+        }
+        Engine* eng = &e;
+        const __half* xp = x.p;
+        __half* cp = col.p;
+        const int N = x.N, H = x.H, Wd = x.W, C = x.C;
+        plan.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_im2col_s2(xp, N, H, Wd, C, pad_lo, Ho, Wo, cp, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+        Act out = alloc(x.N, Ho, Wo, cout);
+        if (!ok) return out;
+        Lin l;
+        l.A0 = col.p;
+        l.lda0 = 9 * x.C;
+        l.K0 = 9 * x.C;
+        l.M = col.rows();
+        l.W = W;
+        l.ldw = kk;
+        l.N = cout;
+        l.bias = F32(p + ".bias");
+        l.out = out.p;
+        linear(l);
+        release(col);
+        return out;
+    }
+
+    // ResnetBlock2D; `skip` is the second source of a channel concat (p == nullptr when absent).
+    Act resnet(const std::string& p, const Act& x, const Act& skip, float eps, const float* conv1_bias_override) {
+        if (!ok) return Act{};
+        const int cin = x.C + (skip.p ? skip.C : 0);
+        Act n1 = groupnorm(x, skip, p + ".norm1", eps, 1);
+        Act h = conv3x3(n1, Act{}, p + ".conv1", conv1_bias_override, nullptr);
+        release(n1);
+        Act n2 = groupnorm(h, Act{}, p + ".norm2", eps, 1);
+        release(h);
+        if (!ok) return Act{};
+        const int cout = n2.C;
+        Act sc;
+        const __half* scp = x.p;
+        if (e.find(prefix + p + ".conv_shortcut.weight")) {
+            sc = like(x, cout);
+            int r = 0, c = 0;
+            Lin l;
+            l.A0 = x.p;
+            l.lda0 = x.C;
+            l.K0 = x.C;
+            if (skip.p) {
+                l.A1 = skip.p;
+                l.lda1 = skip.C;
+                l.K1 = skip.C;
+            }
+            l.M = x.rows();
+            l.W = W16(p + ".conv_shortcut.weight", &r, &c);
+            l.ldw = c;
+            l.N = cout;
+            l.bias = F32(p + ".conv_shortcut.bias");
+            l.out = sc.p;
+            if (ok && c != cin) fail("shortcut weight '" + prefix + p + "' has unexpected K");
+            linear(l);
+            scp = sc.p;
+        } else if (cin != cout) {
+            fail("resnet '" + prefix + p + "' changes channels but has no conv_shortcut");
+        }
+        Act out = conv3x3(n2, Act{}, p + ".conv2", nullptr, scp);
+        release(n2);
+        if (sc.p) release(sc);
+        return out;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Engine: weights
+// ------------------------------------------------------------------------------------------------------------
+Engine::Engine(const dtp_config& cfg) : cfg_(cfg) {
+    if (cfg_.arena_bytes == 0) cfg_.arena_bytes = 8ull << 30;
+    if (cfg_.enc_tokens <= 0) cfg_.enc_tokens = 14;
+}
+
+Engine::~Engine() {
+    for (auto& kv : w_)
+        if (kv.second.dev) cudaFree(kv.second.dev);
+    for (void* p : persistent_) cudaFree(p);
+    if (arena_base_) cudaFree(arena_base_);
+    if (ws_) cudaFree(ws_);
+}
+
+const WT* Engine::find(const std::string& name) {
+    auto it = w_.find(name);
+    return it == w_.end() ? nullptr : &it->second;
+}
+
+void* Engine::persistent(size_t bytes, bool zero) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        err_ = "cudaMalloc(" + std::to_string(bytes) + ") failed";
+        return nullptr;
+    }
+    if (zero) cudaMemset(p, 0, bytes);
+    persistent_.push_back(p);
+    return p;
+}
+
+int Engine::ensure_arena() {
+    if (arena_base_) return 0;
+    if (cudaMalloc(&arena_base_, cfg_.arena_bytes) != cudaSuccess)
+        return fail("cudaMalloc of the " + std::to_string(cfg_.arena_bytes >> 20) + " MiB activation arena failed");
+    arena_.init(arena_base_, cfg_.arena_bytes);
+    return 0;
+}
+
+int Engine::ensure_ws() {
+    if (ws_needed_ <= ws_bytes_) return 0;
+    if (ws_) {
+        cudaDeviceSynchronize();
+        cudaFree(ws_);
+    }
+    ws_ = nullptr;
+    ws_bytes_ = 0;
+    const size_t want = ws_needed_ + (ws_needed_ >> 2);
+    if (cudaMalloc(&ws_, want) != cudaSuccess) return fail("cudaMalloc of the split-K workspace failed");
+    ws_bytes_ = want;
+    return 0;
+}
+
+int Engine::set_tensor(const char* name, const void* host, const int64_t* shape, int ndim, int dtype) {
+    if (!name || !host || ndim < 0 || ndim > 8 || (dtype != 0 && dtype != 1)) return fail("set_tensor: bad arguments");
+    WT t;
+    t.dtype = dtype;
+    t.shape.assign(shape, shape + ndim);
+    const size_t bytes = static_cast<size_t>(t.numel()) * (dtype == 0 ? 4 : 2);
+    if (cudaMalloc(&t.dev, bytes ? bytes : 16) != cudaSuccess)
+        return fail(std::string("set_tensor: cudaMalloc failed for ") + name);
+    if (cudaMemcpy(t.dev, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(t.dev);
+        return fail(std::string("set_tensor: copy failed for ") + name);
+    }
+    if (dtype == 0 && t.numel() <= (1 << 22)) {
+        t.host.assign(static_cast<const float*>(host), static_cast<const float*>(host) + t.numel());
+    }
+    auto it = w_.find(name);
+    if (it != w_.end()) {
+        cudaFree(it->second.dev);
+        w_.erase(it);
+    }
+    w_.emplace(name, std::move(t));
+    finalized_ = false;
+    return 0;
+}
+
+// UNet traversal shared by finalize (inventory) and the plan builder: calls back for each resnet / transformer prefix.
+template <typename FR, typename FT>
+static void walk_unet(const dtp_config& c, FR on_resnet, FT on_transformer) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < c.unet_layers_per_block; ++j) {
+            on_resnet("down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
+            if (c.unet_down_attn[i]) on_transformer("down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j));
+        }
+    on_resnet(std::string("mid_block.resnets.0"));
+    on_transformer(std::string("mid_block.attentions.0"));
+    on_resnet(std::string("mid_block.resnets.1"));
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < c.unet_layers_per_block + 1; ++j) {
+            on_resnet("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j));
+            if (c.unet_down_attn[3 - i]) on_transformer("up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j));
+        }
+}
+
+int Engine::finalize_weights() {
+    if (finalized_) return 0;
+    // inventory of UNet resnets (time-embedding row layout) and transformers (cross-attention K/V slots)
+    resnets_.clear();
+    tf_names_.clear();
+    temb_total_ = 0;
+    bool missing = false;
+    std::string first_missing;
+    walk_unet(
+        cfg_,
+        [&](const std::string& p) {
+            const WT* b = find("unet." + p + ".conv1.bias");
+            const WT* tb = find("unet." + p + ".time_emb_proj.bias");
+            if (!b || !tb || b->host.empty() || tb->host.size() != b->host.size()) {
+                if (!missing) first_missing = "unet." + p + ".{conv1,time_emb_proj}.bias";
+                missing = true;
+                return;
+            }
+            resnets_.push_back({p, temb_total_});
+            temb_total_ += static_cast<int>(b->host.size());
+        },
+        [&](const std::string& p) { tf_names_.push_back(p); });
+    if (missing) return fail("finalize_weights: missing " + first_missing);
+    // combined bias conv1.bias + time_emb_proj.bias (the per-step projection is added by the schedule tables)
+    std::vector<float> comb(temb_total_);
+    for (auto& r : resnets_) {
+        const WT* b = find("unet." + r.first + ".conv1.bias");
+        const WT* tb = find("unet." + r.first + ".time_emb_proj.bias");
+        for (size_t i = 0; i < b->host.size(); ++i) comb[r.second + i] = b->host[i] + tb->host[i];
+    }
+    {
+        WT t;
+        t.dtype = 0;
+        t.shape = {temb_total_};
+        if (cudaMalloc(&t.dev, comb.size() * 4) != cudaSuccess) return fail("finalize_weights: cudaMalloc failed");
+        cudaMemcpy(t.dev, comb.data(), comb.size() * 4, cudaMemcpyHostToDevice);
+        auto it = w_.find("unet.__temb_bias_comb");
+        if (it != w_.end()) {
+            cudaFree(it->second.dev);
+            w_.erase(it);
+        }
+        w_.emplace("unet.__temb_bias_comb", std::move(t));
+    }
+    temb_cur_ = static_cast<float*>(persistent(static_cast<size_t>(temb_total_) * 4, true));
+    if (!temb_cur_) return -1;
+    cross_kv_.assign(tf_names_.size(), nullptr);
+    for (size_t i = 0; i < tf_names_.size(); ++i) {
+        const WT* kvw = find("unet." + tf_names_[i] + ".transformer_blocks.0.attn2.to_kv.weight");
+        if (!kvw) return fail("finalize_weights: missing unet." + tf_names_[i] + ".transformer_blocks.0.attn2.to_kv.weight");
+        cross_kv_[i] = static_cast<__half*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * kvw->shape[0] * 2, true));
+        if (!cross_kv_[i]) return -1;
+    }
+    ctx_ = static_cast<__half*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * cfg_.unet_cross_dim * 2, true));
+    ctx_f32_ = static_cast<float*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * cfg_.unet_cross_dim * 4, true));
+    if (!ctx_ || !ctx_f32_) return -1;
+    unet_plan_.clear();
+    vae_enc_plan_.clear();
+    vae_dec_plan_.clear();
+    enc_plan_.clear();
+    cond_plan_.clear();
+    temb_dirty_ = true;
+    cond_set_ = false;
+    finalized_ = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// UNet plan
+// ------------------------------------------------------------------------------------------------------------
+static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std::string& p, const Act& x, __half* kv,
+                         const int* kv_index) {
+    if (!b.ok) return Act{};
+    const int C = x.C, heads = cfg.unet_heads, d = C / heads;
+    const int seq = x.H * x.W, batch = x.N;
+    const long long rows = x.rows();
+    const std::string t = p + ".transformer_blocks.0";
+    Act n = b.groupnorm(x, Act{}, p + ".norm", 1e-6f, 0);
+    Act h = b.like(x, C);
+    int wr = 0, wc = 0;
+    {
+        Lin l;
+        l.A0 = n.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(p + ".proj_in.weight", &wr, &wc); l.ldw = C; l.N = C;
+        l.bias = b.F32(p + ".proj_in.bias"); l.out = h.p;
+        b.linear(l);
+    }
+    b.release(n);
+    // self-attention
+    Act tmp = b.like(x, C);
+    b.layernorm(h, t + ".norm1", tmp.p);
+    Act qkv = b.like(x, 3 * C);
+    {
+        Lin l;
+        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(t + ".attn1.to_qkv.weight"); l.ldw = C; l.N = 3 * C; l.out = qkv.p;
+        b.linear(l);
+    }
+    b.release(tmp);
+    Act att = b.like(x, C);
+    if (b.ok)
+        b.attention(qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, att.p, C, seq, seq, heads, d, batch,
+                    static_cast<long long>(seq) * 3 * C, static_cast<long long>(seq) * 3 * C,
+                    static_cast<long long>(seq) * C, nullptr);
+    b.release(qkv);
+    {
+        Lin l;
+        l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(t + ".attn1.to_out.0.weight"); l.ldw = C; l.N = C;
+        l.bias = b.F32(t + ".attn1.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+        b.linear(l);
+    }
+    b.release(att);
+    // cross-attention on the (pre-projected) image tokens
+    tmp = b.like(x, C);
+    b.layernorm(h, t + ".norm2", tmp.p);
+    Act q = b.like(x, C);
+    {
+        Lin l;
+        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(t + ".attn2.to_q.weight"); l.ldw = C; l.N = C; l.out = q.p;
+        b.linear(l);
+    }
+    b.release(tmp);
+    att = b.like(x, C);
+    const int T = cfg.enc_tokens;
+    if (b.ok)
+        b.attention(q.p, C, kv, 2 * C, kv + C, 2 * C, att.p, C, seq, T, heads, d, batch, static_cast<long long>(seq) * C,
+                    static_cast<long long>(T) * 2 * C, static_cast<long long>(seq) * C, kv_index);
+    b.release(q);
+    {
+        Lin l;
+        l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(t + ".attn2.to_out.0.weight"); l.ldw = C; l.N = C;
+        l.bias = b.F32(t + ".attn2.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+        b.linear(l);
+    }
+    b.release(att);
+    // GEGLU feed-forward
+    tmp = b.like(x, C);
+    b.layernorm(h, t + ".norm3", tmp.p);
+    Act g = b.like(x, 4 * C);
+    {
+        Lin l;
+        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
+        l.bias = b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
+        b.linear(l);
+    }
+    b.release(tmp);
+    {
+        Lin l;
+        l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
+        l.W = b.W16(t + ".ff.net.2.weight"); l.ldw = 4 * C; l.N = C;
+        l.bias = b.F32(t + ".ff.net.2.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+        b.linear(l);
+    }
+    b.release(g);
+    Act out = b.like(x, C);
+    {
+        Lin l;
+        l.A0 = h.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(p + ".proj_out.weight"); l.ldw = C; l.N = C;
+        l.bias = b.F32(p + ".proj_out.bias"); l.res = x.p; l.ldr = C; l.out = out.p;
+        b.linear(l);
+    }
+    b.release(h);
+    (void)e;
+    return out;
+}
+
+int Engine::build_unet_plan(int B, int R) {
+    if (unet_plan_.key_a == B && unet_plan_.key_b == R) return 0;
+    if (R % 8) return fail("resolution must be a multiple of 8");
+    if (ensure_arena()) return -1;
+    const int Bz = 3 * B, h = R / 8;
+    const size_t need = static_cast<size_t>(Bz) * h * h;
+    if (need > unet_io_cap_) {
+        unet_in_ = static_cast<__half*>(persistent(need * 64 * 2, true));
+        unet_eps_ = static_cast<float*>(persistent(need * cfg_.unet_out_channels * 4, true));
+        if (!unet_in_ || !unet_eps_) return -1;
+        unet_io_cap_ = need;
+    }
+    if (kv_index_B_ != B) {
+        std::vector<int> idx(Bz);
+        for (int i = 0; i < Bz; ++i) idx[i] = i < B ? 0 : 1;
+        kv_index_ = static_cast<int*>(persistent(Bz * sizeof(int), false));
+        if (!kv_index_) return -1;
+        cudaMemcpy(kv_index_, idx.data(), Bz * sizeof(int), cudaMemcpyHostToDevice);
+        kv_index_B_ = B;
+    }
+    unet_plan_.clear();
+    arena_.reset();
+    Builder b(*this, unet_plan_, "unet.");
+    // op 0: select the time-embedding bias row of the step being evaluated
+    unet_plan_.ops.push_back([this](cudaStream_t st) -> int {
+        if (launch_copy_f32(temb_all_ + static_cast<size_t>(cur_step_) * temb_total_, temb_cur_, temb_total_, st)) {
+            err_ = kernels_last_error();
+            return -1;
+        }
+        return 1;
+    });
+    std::map<std::string, int> temb_off, tf_idx;
+    for (auto& r : resnets_) temb_off[r.first] = r.second;
+    for (size_t i = 0; i < tf_names_.size(); ++i) tf_idx[tf_names_[i]] = static_cast<int>(i);
+    auto res = [&](const std::string& p, const Act& x, const Act& skip) {
+        return b.resnet(p, x, skip, 1e-5f, temb_cur_ + temb_off[p]);
+    };
+    auto tf = [&](const std::string& p, const Act& x) {
+        return transformer2d(b, *this, cfg_, p, x, cross_kv_[tf_idx[p]], kv_index_);
+    };
+    Act in;
+    in.p = unet_in_; in.N = Bz; in.H = h; in.W = h; in.C = 64;
+    Act x = b.conv3x3(in, Act{}, "conv_in", nullptr, nullptr);
+    std::vector<Act> skips;
+    skips.push_back(x);
+    for (int i = 0; i < 4 && b.ok; ++i) {
+        for (int j = 0; j < cfg_.unet_layers_per_block && b.ok; ++j) {
+            const std::string rp = "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+            Act y = res(rp, x, Act{});
+            if (cfg_.unet_down_attn[i]) {
+                Act z = tf("down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), y);
+                b.release(y);
+                y = z;
+            }
+            x = y;
+            skips.push_back(x);
+        }
+        if (i != 3 && b.ok) {
+            x = b.downsample(x, "down_blocks." + std::to_string(i) + ".downsamplers.0.conv", 1);
+            skips.push_back(x);
+        }
+    }
+    if (b.ok) {
+        Act y = res("mid_block.resnets.0", x, Act{});
+        Act z = tf("mid_block.attentions.0", y);
+        b.release(y);
+        x = res("mid_block.resnets.1", z, Act{});  // the last down activation stays alive as a skip
+        b.release(z);
+    }
+    for (int i = 0; i < 4 && b.ok; ++i) {
+        for (int j = 0; j < cfg_.unet_layers_per_block + 1 && b.ok; ++j) {
+            Act skip = skips.back();
+            skips.pop_back();
+            Act y = res("up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, skip);
+            b.release(x);
+            b.release(skip);
+            if (cfg_.unet_down_attn[3 - i]) {
+                Act z = tf("up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), y);
+                b.release(y);
+                y = z;
+            }
+            x = y;
+        }
+        if (i != 3 && b.ok) {
+            Act up = b.upsample2x(x);
+            b.release(x);
+            x = b.conv3x3(up, Act{}, "up_blocks." + std::to_string(i) + ".upsamplers.0.conv", nullptr, nullptr);
+            b.release(up);
+        }
+    }
+    if (b.ok) {
+        Act n = b.groupnorm(x, Act{}, "conv_norm_out", 1e-5f, 1);
+        b.release(x);
+        b.conv3x3_into(n, Act{}, "conv_out.weight", b.F32("conv_out.bias"), nullptr, 0, unet_eps_,
+                       cfg_.unet_out_channels, EPI_OUT_F32_NCHW, h * h);
+        b.release(n);
+    }
+    if (!b.ok) {
+        unet_plan_.clear();
+        return -1;
+    }
+    unet_plan_.key_a = B;
+    unet_plan_.key_b = R;
+    return ensure_ws();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// VAE plans
+// ------------------------------------------------------------------------------------------------------------
+static Act vae_attention(Builder& b, const std::string& p, const Act& x) {
+    if (!b.ok) return Act{};
+    const int C = x.C, seq = x.H * x.W;
+    const long long rows = x.rows();
+    Act n = b.groupnorm(x, Act{}, p + ".group_norm", 1e-6f, 0);
+    Act qkv = b.like(x, 3 * C);
+    {
+        Lin l;
+        l.A0 = n.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(p + ".qkv.weight"); l.ldw = C; l.N = 3 * C; l.bias = b.F32(p + ".qkv.bias"); l.out = qkv.p;
+        b.linear(l);
+    }
+    b.release(n);
+    Act att = b.like(x, C);
+    if (b.ok)
+        b.attention(qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, att.p, C, seq, seq, 1, C, x.N,
+                    static_cast<long long>(seq) * 3 * C, static_cast<long long>(seq) * 3 * C,
+                    static_cast<long long>(seq) * C, nullptr);
+    b.release(qkv);
+    Act out = b.like(x, C);
+    {
+        Lin l;
+        l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = b.W16(p + ".proj_attn.weight"); l.ldw = C; l.N = C; l.bias = b.F32(p + ".proj_attn.bias");
+        l.res = x.p; l.ldr = C; l.out = out.p;
+        b.linear(l);
+    }
+    b.release(att);
+    return out;
+}
+
+int Engine::build_vae_enc_plan(int Nb, int R) {
+    if (vae_enc_plan_.key_a == Nb && vae_enc_plan_.key_b == R) return 0;
+    if (R % 8) return fail("resolution must be a multiple of 8");
+    if (ensure_arena()) return -1;
+    const int h = R / 8;
+    const size_t need = static_cast<size_t>(Nb) * R * R;
+    if (need > vae_enc_cap_) {
+        vae_enc_in_ = static_cast<__half*>(persistent(need * 64 * 2, true));
+        vae_moments_ = static_cast<float*>(persistent(static_cast<size_t>(Nb) * 2 * cfg_.vae_latent * h * h * 4, true));
+        if (!vae_enc_in_ || !vae_moments_) return -1;
+        vae_enc_cap_ = need;
+    }
+    vae_enc_plan_.clear();
+    arena_.reset();
+    Builder b(*this, vae_enc_plan_, "vae.");
+    Act in;
+    in.p = vae_enc_in_; in.N = Nb; in.H = R; in.W = R; in.C = 64;
+    Act x = b.conv3x3(in, Act{}, "encoder.conv_in", nullptr, nullptr);
+    for (int i = 0; i < 4 && b.ok; ++i) {
+        for (int j = 0; j < cfg_.vae_layers_per_block && b.ok; ++j) {
+            Act y = b.resnet("encoder.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, Act{},
+                             1e-6f, nullptr);
+            b.release(x);
+            x = y;
+        }
+        if (i != 3 && b.ok) {
+            Act y = b.downsample(x, "encoder.down_blocks." + std::to_string(i) + ".downsamplers.0.conv", 0);
+            b.release(x);
+            x = y;
+        }
+    }
+    if (b.ok) {
+        Act y = b.resnet("encoder.mid_block.resnets.0", x, Act{}, 1e-6f, nullptr);
+        b.release(x);
+        Act z = vae_attention(b, "encoder.mid_block.attentions.0", y);
+        b.release(y);
+        x = b.resnet("encoder.mid_block.resnets.1", z, Act{}, 1e-6f, nullptr);
+        b.release(z);
+        Act n = b.groupnorm(x, Act{}, "encoder.conv_norm_out", 1e-6f, 1);
+        b.release(x);
+        Act mo = b.conv3x3(n, Act{}, "encoder.conv_out", nullptr, nullptr);  // (Nb, h, h, 2*latent) f16
+        b.release(n);
+        Lin l;
+        const int L2 = 2 * cfg_.vae_latent;
+        l.A0 = mo.p; l.lda0 = L2; l.K0 = L2; l.M = mo.rows();
+        l.W = b.W16("quant_conv.weight"); l.ldw = L2; l.N = L2; l.bias = b.F32("quant_conv.bias");
+        l.out = vae_moments_; l.flags = EPI_OUT_F32_NCHW; l.hw_out = h * h;
+        b.linear(l);
+        b.release(mo);
+    }
+    if (!b.ok) {
+        vae_enc_plan_.clear();
+        return -1;
+    }
+    vae_enc_plan_.key_a = Nb;
+    vae_enc_plan_.key_b = R;
+    return ensure_ws();
+}
+
+int Engine::build_vae_dec_plan(int B, int R) {
+    if (vae_dec_plan_.key_a == B && vae_dec_plan_.key_b == R) return 0;
+    if (R % 8) return fail("resolution must be a multiple of 8");
+    if (ensure_arena()) return -1;
+    const int h = R / 8;
+    const size_t need = static_cast<size_t>(B) * R * R;
+    if (need > vae_dec_cap_) {
+        vae_dec_in_ = static_cast<__half*>(persistent(static_cast<size_t>(B) * h * h * 8 * 2, true));
+        vae_dec_out_ = static_cast<float*>(persistent(need * 3 * 4, true));
+        if (!vae_dec_in_ || !vae_dec_out_) return -1;
+        vae_dec_cap_ = need;
+    }
+    vae_dec_plan_.clear();
+    arena_.reset();
+    Builder b(*this, vae_dec_plan_, "vae.");
+    // post_quant_conv (1x1, latent -> latent) writes the first channels of a zero-padded 64-channel NHWC tensor
+    __half* pq = static_cast<__half*>(persistent(static_cast<size_t>(B) * h * h * 64 * 2, true));
+    if (!pq) return -1;
+    {
+        Lin l;
+        l.A0 = vae_dec_in_; l.lda0 = 8; l.K0 = 8; l.M = static_cast<long long>(B) * h * h;
+        l.W = b.W16("post_quant_conv.weight"); l.ldw = 8; l.N = cfg_.vae_latent; l.bias = b.F32("post_quant_conv.bias");
+        l.out = pq; l.ldc = 64;
+        b.linear(l);
+    }
+    Act in;
+    in.p = pq; in.N = B; in.H = h; in.W = h; in.C = 64;
+    Act x = b.conv3x3(in, Act{}, "decoder.conv_in", nullptr, nullptr);
+    if (b.ok) {
+        Act y = b.resnet("decoder.mid_block.resnets.0", x, Act{}, 1e-6f, nullptr);
+        b.release(x);
+        Act z = vae_attention(b, "decoder.mid_block.attentions.0", y);
+        b.release(y);
+        x = b.resnet("decoder.mid_block.resnets.1", z, Act{}, 1e-6f, nullptr);
+        b.release(z);
+    }
+    for (int i = 0; i < 4 && b.ok; ++i) {
+        for (int j = 0; j < cfg_.vae_layers_per_block + 1 && b.ok; ++j) {
+            Act y = b.resnet("decoder.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, Act{}, 1e-6f,
+                             nullptr);
+            b.release(x);
+            x = y;
+        }
+        if (i != 3 && b.ok) {
+            Act up = b.upsample2x(x);
+            b.release(x);
+            x = b.conv3x3(up, Act{}, "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", nullptr, nullptr);
+            b.release(up);
+        }
+    }
+    if (b.ok) {
+        Act n = b.groupnorm(x, Act{}, "decoder.conv_norm_out", 1e-6f, 1);
+        b.release(x);
+        b.conv3x3_into(n, Act{}, "decoder.conv_out.weight", b.F32("decoder.conv_out.bias"), nullptr, 0, vae_dec_out_, 3,
+                       EPI_OUT_F32_NCHW | EPI_IMG01, R * R);
+        b.release(n);
+    }
+    if (!b.ok) {
+        vae_dec_plan_.clear();
+        return -1;
+    }
+    vae_dec_plan_.key_a = B;
+    vae_dec_plan_.key_b = R;
+    return ensure_ws();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// image encoder plan (CLIP ViT-B/32 visual tower + three patch towers), fixed shapes
+// ------------------------------------------------------------------------------------------------------------
+int Engine::build_encoder_plan() {
+    if (enc_plan_.key_a == 1) return 0;
+    if (ensure_arena()) return -1;
+    const int T = cfg_.enc_tokens, w = cfg_.enc_width;
+    if (!enc_in_copy_) {
+        enc_in_copy_ = static_cast<float*>(persistent(static_cast<size_t>(T) * 3 * 224 * 224 * 4, true));
+        enc_out_ = static_cast<float*>(persistent(static_cast<size_t>(T) * cfg_.enc_cross_dim * 4, true));
+        if (!enc_in_copy_ || !enc_out_) return -1;
+    }
+    enc_plan_.clear();
+    arena_.reset();
+    Builder b(*this, enc_plan_, "enc.");
+    Engine* eng = this;
+    const std::string v = "clip.visual";
+    Act pat = b.alloc(T, 49, 1, 3072);
+    if (b.ok) {
+        const float* src = enc_in_copy_;
+        __half* dst = pat.p;
+        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_patchify32(src, T, dst, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+    }
+    Act tok = b.alloc(T, 49, 1, w);
+    {
+        Lin l;
+        l.A0 = pat.p; l.lda0 = 3072; l.K0 = 3072; l.M = static_cast<long long>(T) * 49;
+        l.W = b.W16(v + ".conv1.weight"); l.ldw = 3072; l.N = w; l.out = tok.p;
+        b.linear(l);
+    }
+    b.release(pat);
+    Act x = b.alloc(T, 50, 1, w);
+    if (b.ok) {
+        const float* cls = b.F32(v + ".class_embedding");
+        const float* pos = b.F32(v + ".positional_embedding");
+        const __half* tp = tok.p;
+        __half* xp = x.p;
+        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_clip_embed(tp, cls, pos, T, w, xp, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+    }
+    b.release(tok);
+    Act tmp = b.like(x, w);
+    b.layernorm(x, v + ".ln_pre", tmp.p);
+    b.release(x);
+    x = tmp;
+    const long long rows = x.rows();
+    const int heads = cfg_.enc_heads, d = w / heads;
+    for (int i = 0; i < cfg_.enc_layers && b.ok; ++i) {
+        const std::string r = v + ".transformer.resblocks." + std::to_string(i);
+        Act t = b.like(x, w);
+        b.layernorm(x, r + ".ln_1", t.p);
+        Act qkv = b.like(x, 3 * w);
+        {
+            Lin l;
+            l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = rows;
+            l.W = b.W16(r + ".attn.in_proj_weight"); l.ldw = w; l.N = 3 * w; l.bias = b.F32(r + ".attn.in_proj_bias");
+            l.out = qkv.p;
+            b.linear(l);
+        }
+        if (b.ok)
+            b.attention(qkv.p, 3 * w, qkv.p + w, 3 * w, qkv.p + 2 * w, 3 * w, t.p, w, 50, 50, heads, d, T, 50LL * 3 * w,
+                        50LL * 3 * w, 50LL * w, nullptr);
+        b.release(qkv);
+        {
+            Lin l;
+            l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = rows;
+            l.W = b.W16(r + ".attn.out_proj.weight"); l.ldw = w; l.N = w; l.bias = b.F32(r + ".attn.out_proj.bias");
+            l.res = x.p; l.ldr = w; l.out = x.p;
+            b.linear(l);
+        }
+        b.layernorm(x, r + ".ln_2", t.p);
+        Act m = b.like(x, cfg_.enc_mlp);
+        {
+            Lin l;
+            l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = rows;
+            l.W = b.W16(r + ".mlp.c_fc.weight"); l.ldw = w; l.N = cfg_.enc_mlp; l.bias = b.F32(r + ".mlp.c_fc.bias");
+            l.out = m.p; l.flags = EPI_QUICKGELU;
+            b.linear(l);
+        }
+        b.release(t);
+        {
+            Lin l;
+            l.A0 = m.p; l.lda0 = cfg_.enc_mlp; l.K0 = cfg_.enc_mlp; l.M = rows;
+            l.W = b.W16(r + ".mlp.c_proj.weight"); l.ldw = cfg_.enc_mlp; l.N = w; l.bias = b.F32(r + ".mlp.c_proj.bias");
+            l.res = x.p; l.ldr = w; l.out = x.p;
+            b.linear(l);
+        }
+        b.release(m);
+    }
+    // ln_post on the class tokens (row n*50), then + pos_emb (the reference's view-scrambled table, uploaded as enc.pos_emb)
+    Act cls = b.alloc(T, 1, 1, w);
+    Act lat = b.alloc(T, 1, 1, w);
+    if (b.ok) {
+        std::vector<int> idx(T);
+        for (int i = 0; i < T; ++i) idx[i] = i * 50;
+        int* didx = static_cast<int*>(persistent(T * sizeof(int), false));
+        if (!didx) return -1;
+        cudaMemcpy(didx, idx.data(), T * sizeof(int), cudaMemcpyHostToDevice);
+        const __half* xp = x.p;
+        __half* cp = cls.p;
+        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+            if (launch_gather_rows(xp, w, didx, T, w, cp, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
+        b.layernorm(cls, v + ".ln_post", lat.p);
+        const float* pe = b.F32("pos_emb");
+        __half* lp = lat.p;
+        if (b.ok)
+            enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+                if (launch_add_rows_bcast(lp, pe, T, w, T, st)) {
+                    eng->err_ = kernels_last_error();
+                    return -1;
+                }
+                return 1;
+            });
+    }
+    b.release(x);
+    b.release(cls);
+    // three towers over token ranges [0,1), [1,5), [5,14) (image_encoder.py:83-92)
+    const char* tower_names[3] = {"l", "m", "s"};
+    const int th = cfg_.enc_tower_heads, td = w / th;
+    int row0 = 0;
+    for (int tw = 0; tw < 3 && b.ok; ++tw) {
+        const int n = (tw == 0) ? 1 : (tw == 1 ? 4 : 9);
+        Act xs;
+        xs.p = lat.p + static_cast<long long>(row0) * w; xs.N = 1; xs.H = n; xs.W = 1; xs.C = w;
+        for (int i = 0; i < cfg_.enc_tower_layers && b.ok; ++i) {
+            const std::string r = std::string(tower_names[tw]) + "_patch_encoder_layers." + std::to_string(i);
+            Act t = b.like(xs, w);
+            b.layernorm(xs, r + ".norm1", t.p);
+            Act qkv = b.like(xs, 3 * w);
+            {
+                Lin l;
+                l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = n;
+                l.W = b.W16(r + ".attn1.to_qkv.weight"); l.ldw = w; l.N = 3 * w; l.bias = b.F32(r + ".attn1.to_qkv.bias");
+                l.out = qkv.p;
+                b.linear(l);
+            }
+            if (b.ok)
+                b.attention(qkv.p, 3 * w, qkv.p + w, 3 * w, qkv.p + 2 * w, 3 * w, t.p, w, n, n, th, td, 1, 0, 0, 0,
+                            nullptr);
+            b.release(qkv);
+            {
+                Lin l;
+                l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = n;
+                l.W = b.W16(r + ".attn1.to_out.0.weight"); l.ldw = w; l.N = w; l.bias = b.F32(r + ".attn1.to_out.0.bias");
+                l.res = xs.p; l.ldr = w; l.out = xs.p;
+                b.linear(l);
+            }
+            b.layernorm(xs, r + ".norm3", t.p);
+            Act m = b.like(xs, 4 * w);
+            {
+                Lin l;
+                l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = n;
+                l.W = b.W16(r + ".ff.net.0.proj.weight"); l.ldw = w; l.N = 4 * w; l.bias = b.F32(r + ".ff.net.0.proj.bias");
+                l.out = m.p; l.flags = EPI_GELU;
+                b.linear(l);
+            }
+            b.release(t);
+            {
+                Lin l;
+                l.A0 = m.p; l.lda0 = 4 * w; l.K0 = 4 * w; l.M = n;
+                l.W = b.W16(r + ".ff.net.2.weight"); l.ldw = 4 * w; l.N = w; l.bias = b.F32(r + ".ff.net.2.bias");
+                l.res = xs.p; l.ldr = w; l.out = xs.p;
+                b.linear(l);
+            }
+            b.release(m);
+        }
+        row0 += n;
+    }
+    if (b.ok) {
+        Act t = b.like(lat, w);
+        b.layernorm(lat, "final_layer_norm", t.p);
+        Lin l;
+        l.A0 = t.p; l.lda0 = w; l.K0 = w; l.M = T;
+        l.W = b.W16("proj_out.weight"); l.ldw = w; l.N = cfg_.enc_cross_dim; l.bias = b.F32("proj_out.bias");
+        l.out = enc_out_; l.flags = EPI_OUT_F32;
+        b.linear(l);
+        b.release(t);
+    }
+    b.release(lat);
+    if (!b.ok) {
+        enc_plan_.clear();
+        return -1;
+    }
+    enc_plan_.key_a = 1;
+    return ensure_ws();
+}
+
+int Engine::encode_patches(const float* patches, float* emb_out, cudaStream_t st) {
+    if (!finalized_ && finalize_weights()) return -1;
+    if (build_encoder_plan()) return -1;
+    const size_t n = static_cast<size_t>(cfg_.enc_tokens) * 3 * 224 * 224;
+    if (cudaMemcpyAsync(enc_in_copy_, patches, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("encode_patches: input copy failed");
+    if (enc_plan_.run(st, &launches_)) return -1;
+    if (cudaMemcpyAsync(emb_out, enc_out_, static_cast<size_t>(cfg_.enc_tokens) * cfg_.enc_cross_dim * 4,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("encode_patches: output copy failed");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// condition: fp16 cast of [uncond | cond] and the cross-attention K/V of every transformer layer
+// ------------------------------------------------------------------------------------------------------------
+int Engine::build_cond_plan() {
+    if (cond_plan_.key_a == 1) return 0;
+    cond_plan_.clear();
+    Builder b(*this, cond_plan_, "unet.");
+    const int T = cfg_.enc_tokens, D = cfg_.unet_cross_dim;
+    Engine* eng = this;
+    cond_plan_.ops.push_back([=](cudaStream_t st) -> int {
+        if (launch_f32_to_f16(eng->ctx_f32_, eng->ctx_, static_cast<long long>(2) * T * D, st)) {
+            eng->err_ = kernels_last_error();
+            return -1;
+        }
+        return 1;
+    });
+    for (size_t i = 0; i < tf_names_.size() && b.ok; ++i) {
+        int r = 0, c = 0;
+        Lin l;
+        l.A0 = ctx_; l.lda0 = D; l.K0 = D; l.M = 2 * T;
+        l.W = b.W16(tf_names_[i] + ".transformer_blocks.0.attn2.to_kv.weight", &r, &c);
+        l.ldw = D; l.N = r; l.out = cross_kv_[i];
+        if (b.ok && c != D) b.fail("attn2.to_kv weight has unexpected K");
+        b.linear(l);
+    }
+    if (!b.ok) {
+        cond_plan_.clear();
+        return -1;
+    }
+    cond_plan_.key_a = 1;
+    return ensure_ws();
+}
+
+int Engine::set_condition(const float* emb, const float* uncond, cudaStream_t st) {
+    if (!finalized_ && finalize_weights()) return -1;
+    if (build_cond_plan()) return -1;
+    const size_t n = static_cast<size_t>(cfg_.enc_tokens) * cfg_.unet_cross_dim;
+    if (cudaMemcpyAsync(ctx_f32_, uncond, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(ctx_f32_ + n, emb, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("set_condition: copy failed");
+    if (cond_plan_.run(st, &launches_)) return -1;
+    cond_set_ = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// schedule: per-evaluation time-embedding bias rows
+// ------------------------------------------------------------------------------------------------------------
+int Engine::set_schedule(int n, const float* ts, const float* a_t, const float* a_prev, float cfg, float tg,
+                         int tg_steps) {
+    if (n < 0 || n > 1000) return fail("set_schedule: bad evaluation count");
+    const bool same = (n == n_steps_) && std::equal(ts, ts + n, ts_.begin());
+    ts_.assign(ts, ts + n);
+    a_t_.assign(a_t, a_t + n);
+    a_prev_.assign(a_prev, a_prev + n);
+    n_steps_ = n;
+    cfg_w_ = cfg;
+    tg_w_ = tg;
+    tg_steps_ = tg_steps;
+    if (!same) temb_dirty_ = true;
+    return 0;
+}
+
+int Engine::build_temb_tables(cudaStream_t st) {
+    if (!temb_dirty_) return 0;
+    if (!finalized_ && finalize_weights()) return -1;
+    const int n = n_steps_;
+    if (n == 0) {
+        temb_dirty_ = false;
+        return 0;
+    }
+    if (n > temb_cap_steps_) {
+        temb_all_ = static_cast<float*>(persistent(static_cast<size_t>(n) * temb_total_ * 4, true));
+        if (!temb_all_) return -1;
+        temb_cap_steps_ = n;
+    }
+    const int c0 = cfg_.unet_block_out[0], Tdim = 4 * c0;
+    float* d_ts = nullptr;
+    __half *e16 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    if (cudaMalloc(&d_ts, n * 4) != cudaSuccess || cudaMalloc(&e16, static_cast<size_t>(n) * c0 * 2) != cudaSuccess ||
+        cudaMalloc(&t1, static_cast<size_t>(n) * Tdim * 2) != cudaSuccess ||
+        cudaMalloc(&t2, static_cast<size_t>(n) * Tdim * 2) != cudaSuccess)
+        return fail("schedule tables: cudaMalloc failed");
+    cudaMemcpyAsync(d_ts, ts_.data(), n * 4, cudaMemcpyHostToDevice, st);
+    Plan p;
+    Builder b(*this, p, "unet.");
+    Engine* eng = this;
+    p.ops.push_back([=](cudaStream_t s) -> int {
+        if (launch_timestep_embedding(d_ts, n, c0, e16, s)) {
+            eng->err_ = kernels_last_error();
+            return -1;
+        }
+        return 1;
+    });
+    {
+        Lin l;
+        l.A0 = e16; l.lda0 = c0; l.K0 = c0; l.M = n;
+        l.W = b.W16("time_embedding.linear_1.weight"); l.ldw = c0; l.N = Tdim;
+        l.bias = b.F32("time_embedding.linear_1.bias"); l.out = t1; l.flags = EPI_SILU;
+        b.linear(l);
+    }
+    {
+        // every consumer applies SiLU to temb before its projection (ResnetBlock2D), so fold it here
+        Lin l;
+        l.A0 = t1; l.lda0 = Tdim; l.K0 = Tdim; l.M = n;
+        l.W = b.W16("time_embedding.linear_2.weight"); l.ldw = Tdim; l.N = Tdim;
+        l.bias = b.F32("time_embedding.linear_2.bias"); l.out = t2; l.flags = EPI_SILU;
+        b.linear(l);
+    }
+    const float* comb = b.F32("__temb_bias_comb");
+    for (auto& r : resnets_) {
+        if (!b.ok) break;
+        int rr = 0, cc = 0;
+        Lin l;
+        l.A0 = t2; l.lda0 = Tdim; l.K0 = Tdim; l.M = n;
+        l.W = b.W16(r.first + ".time_emb_proj.weight", &rr, &cc); l.ldw = Tdim; l.N = rr;
+        l.bias = comb + r.second; l.out = temb_all_ + r.second; l.ldc = temb_total_; l.flags = EPI_OUT_F32;
+        b.linear(l);
+    }
+    int rc = b.ok ? 0 : -1;
+    if (rc == 0) rc = ensure_ws();
+    if (rc == 0) rc = p.run(st, &launches_);
+    cudaStreamSynchronize(st);
+    cudaFree(d_ts);
+    cudaFree(e16);
+    cudaFree(t1);
+    cudaFree(t2);
+    if (rc == 0) temb_dirty_ = false;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// stage entry points and the stamp driver
+// ------------------------------------------------------------------------------------------------------------
+#define KCHECK(call)                       \
+    do {                                   \
+        if ((call) != 0) {                 \
+            err_ = kernels_last_error();   \
+            return -1;                     \
+        }                                  \
+        ++launches_;                       \
+    } while (0)
+
+int Engine::vae_encode(int Nb, int R, const float* images, const float* noise, float* latents_out, cudaStream_t st) {
+    if (!finalized_ && finalize_weights()) return -1;
+    if (build_vae_enc_plan(Nb, R)) return -1;
+    const int h = R / 8;
+    KCHECK(launch_nchw_to_nhwc_pad(images, Nb, 3, R * R, 64, 1.0f, vae_enc_in_, st));
+    if (vae_enc_plan_.run(st, &launches_)) return -1;
+    KCHECK(launch_vae_sample(vae_moments_, noise, Nb, h * h, 0.18215f, latents_out, st));
+    return 0;
+}
+
+int Engine::vae_decode(int B, int R, const float* latents, float* images_out, cudaStream_t st) {
+    if (!finalized_ && finalize_weights()) return -1;
+    if (build_vae_dec_plan(B, R)) return -1;
+    const int h = R / 8;
+    KCHECK(launch_nchw_to_nhwc_pad(latents, B, cfg_.vae_latent, h * h, 8, 0.18215f, vae_dec_in_, st));
+    if (vae_dec_plan_.run(st, &launches_)) return -1;
+    if (images_out != vae_dec_out_)
+        KCHECK(launch_copy_f32(vae_dec_out_, images_out, static_cast<long long>(B) * 3 * R * R, st));
+    return 0;
+}
+
+int Engine::unet_forward(int B, int R, const float* sample, const float* latents, const float* mask3,
+                         const float* masked3, int step, float* eps_out, cudaStream_t st) {
+    if (!finalized_ && finalize_weights()) return -1;
+    if (!cond_set_) return fail("unet_forward: call dtp_set_condition first");
+    if (step < 0 || step >= n_steps_) return fail("unet_forward: step outside the schedule");
+    if (build_temb_tables(st)) return -1;
+    if (build_unet_plan(B, R)) return -1;
+    const int h = R / 8, Bz = 3 * B;
+    if (sample) {
+        KCHECK(launch_nchw_to_nhwc_pad(sample, Bz, cfg_.unet_in_channels, h * h, 64, 1.0f, unet_in_, st));
+    } else {
+        KCHECK(launch_pack_unet_input(latents, mask3, masked3, B, h * h, unet_in_, st));
+    }
+    cur_step_ = step;
+    if (unet_plan_.run(st, &launches_)) return -1;
+    if (eps_out && eps_out != unet_eps_)
+        KCHECK(launch_copy_f32(unet_eps_, eps_out, static_cast<long long>(Bz) * cfg_.unet_out_channels * h * h, st));
+    return 0;
+}
+
+int Engine::ensure_io(int B, int R) {
+    if (static_cast<size_t>(B) <= io_cap_B_ && static_cast<size_t>(R) <= io_cap_R_) return 0;
+    const size_t b = std::max<size_t>(B, io_cap_B_), r = std::max<size_t>(R, io_cap_R_);
+    const size_t hw = (r / 8) * (r / 8);
+    lat_ = static_cast<float*>(persistent(b * 4 * hw * 4, true));
+    mask3_ = static_cast<float*>(persistent(3 * b * hw * 4, true));
+    masked3_ = static_cast<float*>(persistent(3 * b * 4 * hw * 4, true));
+    lat2_ = static_cast<float*>(persistent(2 * b * 4 * hw * 4, true));
+    // canvas pre-process outputs: masked (3), mask (1), ctx (3), ctx mask (1), scratch (1), raw result (3), images x2 (6)
+    pre_ = static_cast<float*>(persistent(b * 18 * r * r * 4, true));
+    if (!lat_ || !mask3_ || !masked3_ || !lat2_ || !pre_) return -1;
+    io_cap_B_ = b;
+    io_cap_R_ = r;
+    return 0;
+}
+
+int Engine::infer(int B, int R, const float* masked_img, const float* mask, const float* ctx_img, const float* ctx_mask,
+                  const float* init_latents, const float* vae_noise, float* out_images, cudaStream_t st) {
+    if (B < 1 || R < 8 || (R % 8)) return fail("infer: bad batch / resolution");
+    if (!finalized_ && finalize_weights()) return -1;
+    if (!cond_set_) return fail("infer: call dtp_set_condition first");
+    if (ensure_io(B, R)) return -1;
+    if (build_temb_tables(st)) return -1;
+    const int h = R / 8, hw = h * h;
+    const size_t img = static_cast<size_t>(B) * 3 * R * R;
+    // both VAE encodes (masked image, context image) as one batch of 2B (inpaint_pipeline.py:125-126)
+    float* both = pre_ + static_cast<size_t>(B) * 12 * R * R;
+    KCHECK(launch_copy_f32(masked_img, both, img, st));
+    KCHECK(launch_copy_f32(ctx_img, both + img, img, st));
+    if (vae_encode(2 * B, R, both, vae_noise, lat2_, st)) return -1;
+    // masks: nearest /8, stacked [mask, mask, ctx_mask]; masked latents [ml, ml, cml] (inpaint_pipeline.py:114-116,136)
+    KCHECK(launch_mask_nearest(mask, B, R, 8, mask3_, st));
+    KCHECK(launch_copy_f32(mask3_, mask3_ + static_cast<size_t>(B) * hw, static_cast<long long>(B) * hw, st));
+    KCHECK(launch_mask_nearest(ctx_mask, B, R, 8, mask3_ + static_cast<size_t>(2) * B * hw, st));
+    const long long l4 = static_cast<long long>(B) * 4 * hw;
+    KCHECK(launch_copy_f32(lat2_, masked3_, l4, st));
+    KCHECK(launch_copy_f32(lat2_, masked3_ + l4, l4, st));
+    KCHECK(launch_copy_f32(lat2_ + l4, masked3_ + 2 * l4, l4, st));
+    KCHECK(launch_copy_f32(init_latents, lat_, l4, st));
+    // denoising loop (stable_diffusion_pipeline.py:407-462)
+    for (int i = 0; i < n_steps_; ++i) {
+        const float tg = (i > tg_steps_ - 1) ? 0.0f : tg_w_;
+        if (unet_forward(B, R, nullptr, lat_, mask3_, masked3_, i, nullptr, st)) return -1;
+        KCHECK(launch_guidance_ddim(unet_eps_, lat_, lat_, B, 4 * hw, cfg_w_, tg, a_t_[i], a_prev_[i], st));
+    }
+    if (vae_decode(B, R, lat_, out_images, st)) return -1;
+    ++stamps_;
+    return 0;
+}
+
+int Engine::stamp(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+                  const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st) {
+    if (B < 1 || R < 8 || (R % 8)) return fail("stamp: bad batch / resolution");
+    if (ensure_io(B, R)) return -1;
+    const size_t plane = static_cast<size_t>(B) * R * R;
+    float* masked = pre_;
+    float* mask = pre_ + 3 * plane;
+    float* ctx = pre_ + 4 * plane;
+    float* cmask = pre_ + 7 * plane;
+    float* scratch = pre_ + 8 * plane;
+    float* raw = pre_ + 9 * plane;
+    if (launch_canvas_preprocess(canvas, brush, B, R, pad, masked, mask, ctx, cmask, scratch, st)) {
+        err_ = kernels_last_error();
+        return -1;
+    }
+    launches_ += 2;
+    float* dst = (composite || out_f32 == nullptr) ? raw : out_f32;
+    if (infer(B, R, masked, mask, ctx, cmask, init_latents, vae_noise, dst, st)) return -1;
+    if (composite || out_u8) {
+        if (composite) {
+            KCHECK(launch_composite(canvas, raw, B, R, out_f32, out_u8, st));
+        } else {
+            return fail("stamp: uint8 output is only produced together with compositing");
+        }
+    }
+    return 0;
+}
+
+long long Engine::counter(const char* name) const {
+    const std::string n = name ? name : "";
+    if (n == "launches") return launches_;
+    if (n == "stamps") return stamps_;
+    if (n == "arena_peak") return static_cast<long long>(arena_.peak());
+    if (n == "arena_bytes") return static_cast<long long>(cfg_.arena_bytes);
+    if (n == "unet_plan_ops") return static_cast<long long>(unet_plan_.ops.size());
+    if (n == "ws_bytes") return static_cast<long long>(ws_bytes_);
+    return -1;
+}
+
+int Engine::set_option(const char* name, int value) {
+    const std::string n = name ? name : "";
+    if (n == "sync_check") {
+        opt_sync_check_ = value;
+        return 0;
+    }
+    return fail("unknown option " + n);
+}
+
+}  // namespace dtp
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+using dtp::Engine;
+struct dtp_engine {
+    Engine* e;
+};
+static char g_create_err[256] = "";
+
+extern "C" {
+
+int dtp_create(const dtp_config* cfg, dtp_handle** out) {
+    if (!cfg || !out) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "no CUDA device");
+        return -2;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err), "device sm_%d%d is not sm_100: this library is Blackwell-only",
+                 prop.major, prop.minor);
+        return -3;
+    }
+    dtp_handle* h = new dtp_engine;
+    h->e = new Engine(*cfg);
+    *out = h;
+    return 0;
+}
+void dtp_destroy(dtp_handle* h) {
+    if (!h) return;
+    delete h->e;
+    delete h;
+}
+const char* dtp_last_error(dtp_handle* h) { return h ? h->e->last_error() : g_create_err; }
+int dtp_set_tensor(dtp_handle* h, const char* name, const void* host_ptr, const long long* shape, int ndim, int dtype) {
+    return h->e->set_tensor(name, host_ptr, reinterpret_cast<const int64_t*>(shape), ndim, dtype);
+}
+int dtp_finalize_weights(dtp_handle* h) { return h->e->finalize_weights(); }
+int dtp_encode_patches(dtp_handle* h, const float* patches, float* emb_out, void* stream, void*) {
+    return h->e->encode_patches(patches, emb_out, (cudaStream_t)stream);
+}
+int dtp_set_condition(dtp_handle* h, const float* emb, const float* uncond, void* stream) {
+    return h->e->set_condition(emb, uncond, (cudaStream_t)stream);
+}
+int dtp_set_schedule(dtp_handle* h, int n, const float* timesteps, const float* alpha_t, const float* alpha_prev,
+                     float cfg, float tg, int tg_steps) {
+    return h->e->set_schedule(n, timesteps, alpha_t, alpha_prev, cfg, tg, tg_steps);
+}
+int dtp_infer(dtp_handle* h, int B, int R, const float* masked_img, const float* mask, const float* ctx_img,
+              const float* ctx_mask, const float* init_latents, const float* vae_noise, float* out_images, void* stream) {
+    return h->e->infer(B, R, masked_img, mask, ctx_img, ctx_mask, init_latents, vae_noise, out_images,
+                       (cudaStream_t)stream);
+}
+int dtp_stamp(dtp_handle* h, int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+              const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, void* stream) {
+    return h->e->stamp(B, R, canvas, brush, pad, init_latents, vae_noise, composite, out_f32, out_u8,
+                       (cudaStream_t)stream);
+}
+int dtp_vae_encode(dtp_handle* h, int Nb, int R, const float* images, const float* noise, float* latents_out,
+                   void* stream) {
+    return h->e->vae_encode(Nb, R, images, noise, latents_out, (cudaStream_t)stream);
+}
+int dtp_vae_decode(dtp_handle* h, int B, int R, const float* latents, float* images_out, void* stream) {
+    return h->e->vae_decode(B, R, latents, images_out, (cudaStream_t)stream);
+}
+int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const float*, const float*, int step,
+                     float* eps_out, void* stream) {
+    return h->e->unet_forward(B, R, sample, nullptr, nullptr, nullptr, step, eps_out, (cudaStream_t)stream);
+}
+long long dtp_get_counter(dtp_handle* h, const char* name) { return h->e->counter(name); }
+int dtp_set_option(dtp_handle* h, const char* name, int value) { return h->e->set_option(name, value); }
+
+}  // extern "C"

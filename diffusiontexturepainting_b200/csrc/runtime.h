@@ -1,0 +1,168 @@
+// Native runtime of the stamp path: weight store, activation arena, launch plans (UNet / VAE / image encoder) and the
+// per-stamp driver. Replaces the TensorRT engine layer of the reference (trt_inference/utilities.py:54-264 Engine,
+// stable_diffusion_pipeline.py:189-338 loadEngines/runEngine) and the graphs of trt_inference/models.py.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dtp.h"
+#include "gemm_tc.h"
+
+namespace dtp {
+
+struct WT {  // one named weight tensor
+    void* dev = nullptr;
+    std::vector<int64_t> shape;
+    int dtype = 0;  // 0 = f32, 1 = f16
+    std::vector<float> host;  // host copy of f32 tensors (small: biases, norm affine, embeddings)
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// First-fit offset allocator over one device slab; plans carve their transient activations from it at build time.
+class Arena {
+   public:
+    void init(char* base, size_t cap) {
+        base_ = base;
+        cap_ = cap;
+        reset();
+    }
+    void reset() {
+        free_.clear();
+        free_[0] = cap_;
+        used_ = peak_ = 0;
+    }
+    void* alloc(size_t bytes);
+    void release(void* p);
+    size_t peak() const { return peak_; }
+    size_t capacity() const { return cap_; }
+
+   private:
+    char* base_ = nullptr;
+    size_t cap_ = 0, used_ = 0, peak_ = 0;
+    std::map<size_t, size_t> free_;                 // offset -> size
+    std::unordered_map<size_t, size_t> live_;       // offset -> size
+};
+
+struct Act {  // NHWC fp16 activation: rows = N*H*W pixels, C channels
+    __half* p = nullptr;
+    int N = 0, H = 0, W = 0, C = 0;
+    long long rows() const { return static_cast<long long>(N) * H * W; }
+    size_t bytes() const { return static_cast<size_t>(rows()) * C * sizeof(__half); }
+};
+
+struct Plan {
+    std::vector<std::function<int(cudaStream_t)>> ops;
+    int key_a = -1, key_b = -1;  // (batch, resolution) the plan was built for
+    int run(cudaStream_t st, long long* launch_counter) const;
+    void clear() {
+        ops.clear();
+        key_a = key_b = -1;
+    }
+};
+
+class Engine {
+   public:
+    explicit Engine(const dtp_config& cfg);
+    ~Engine();
+
+    int set_tensor(const char* name, const void* host, const int64_t* shape, int ndim, int dtype);
+    int finalize_weights();
+    int encode_patches(const float* patches, float* emb_out, cudaStream_t st);
+    int set_condition(const float* emb, const float* uncond, cudaStream_t st);
+    int set_schedule(int n, const float* ts, const float* a_t, const float* a_prev, float cfg, float tg, int tg_steps);
+    int infer(int B, int R, const float* masked_img, const float* mask, const float* ctx_img, const float* ctx_mask,
+              const float* init_latents, const float* vae_noise, float* out_images, cudaStream_t st);
+    int stamp(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+              const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st);
+    int vae_encode(int Nb, int R, const float* images, const float* noise, float* latents_out, cudaStream_t st);
+    int vae_decode(int B, int R, const float* latents, float* images_out, cudaStream_t st);
+    int unet_forward(int B, int R, const float* sample, const float* latents, const float* mask3, const float* masked3,
+                     int step, float* eps_out, cudaStream_t st);
+    long long counter(const char* name) const;
+    int set_option(const char* name, int value);
+    const char* last_error() const { return err_.c_str(); }
+
+   private:
+    friend struct Builder;
+    int fail(const std::string& msg) {
+        err_ = msg;
+        return -1;
+    }
+    const WT* find(const std::string& name);
+    void* persistent(size_t bytes, bool zero);
+    int ensure_arena();
+    int build_unet_plan(int B, int R);
+    int build_vae_enc_plan(int Nb, int R);
+    int build_vae_dec_plan(int B, int R);
+    int build_encoder_plan();
+    int build_cond_plan();
+    int build_temb_tables(cudaStream_t st);
+    int ensure_ws();
+    int ensure_io(int B, int R);
+
+    dtp_config cfg_;
+    std::unordered_map<std::string, WT> w_;
+    std::vector<void*> persistent_;
+    bool finalized_ = false;
+    std::string err_;
+
+    char* arena_base_ = nullptr;
+    Arena arena_;
+    float* ws_ = nullptr;  // split-K workspace shared by all contractions (stream-ordered reuse)
+    size_t ws_bytes_ = 0, ws_needed_ = 0;
+
+    Plan unet_plan_, vae_enc_plan_, vae_dec_plan_, enc_plan_, cond_plan_;
+    // plan I/O (persistent)
+    __half* unet_in_ = nullptr;      // (3B, h, h, 64) packed sample
+    float* unet_eps_ = nullptr;      // (3B, 4, h, h)
+    __half* vae_enc_in_ = nullptr;   // (Nb, R, R, 64)
+    float* vae_moments_ = nullptr;   // (Nb, 8, h, h)
+    __half* vae_dec_in_ = nullptr;   // (B, h, h, 8)
+    float* vae_dec_out_ = nullptr;   // (B, 3, R, R)
+    size_t unet_io_cap_ = 0, vae_enc_cap_ = 0, vae_dec_cap_ = 0;
+    int* kv_index_ = nullptr;
+    int kv_index_B_ = -1;
+    // per-infer scratch (persistent, sized by ensure_io)
+    float *lat_ = nullptr, *mask3_ = nullptr, *masked3_ = nullptr, *lat2_ = nullptr, *pre_ = nullptr;
+    size_t io_cap_B_ = 0, io_cap_R_ = 0;
+
+    // encoder plan I/O
+    float* enc_patches_ = nullptr;  // borrowed per call
+    float* enc_in_copy_ = nullptr;  // (14,3,224,224) staging so the plan has a fixed address
+    float* enc_out_ = nullptr;      // (14, cross) f32
+
+    // condition
+    __half* ctx_ = nullptr;  // (2*14, cross) f16: rows 0..13 uncond, 14..27 cond
+    float* ctx_f32_ = nullptr;
+    std::vector<__half*> cross_kv_;  // per transformer layer: (28, 2C)
+    std::vector<std::string> tf_names_;  // transformer prefixes in execution order
+    bool cond_set_ = false;
+
+    // schedule
+    int n_steps_ = 0, tg_steps_ = 0;
+    float cfg_w_ = 2.0f, tg_w_ = 0.0f;
+    std::vector<float> ts_, a_t_, a_prev_;
+    float* temb_all_ = nullptr;   // (n_steps, temb_total) f32: conv1.bias + time_emb_proj(SiLU(temb_s)) per resnet
+    float* temb_cur_ = nullptr;   // (temb_total) row of the step being evaluated
+    int temb_total_ = 0;
+    int temb_cap_steps_ = 0;
+    std::vector<std::pair<std::string, int>> resnets_;  // UNet resnet prefix -> offset into the temb row
+    int cur_step_ = 0;
+    bool temb_dirty_ = true;
+
+    long long launches_ = 0, stamps_ = 0;
+    int opt_sync_check_ = 0;
+};
+
+}  // namespace dtp

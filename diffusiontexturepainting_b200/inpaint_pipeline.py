@@ -1,0 +1,64 @@
+"""Drop-in for trt_inference/inpaint_pipeline.py: InpaintPipeline.{update_infer_settings, infer} with the reference's
+signatures and loop semantics (t_start = 1 quirk included), executed by the native engine."""
+from __future__ import annotations
+
+import torch
+
+from .stable_diffusion_pipeline import StableDiffusionPipeline
+
+
+class InpaintPipeline(StableDiffusionPipeline):
+    def __init__(self, scheduler="DDIM", *args, **kwargs):
+        super().__init__(*args, **kwargs, inpaint=True, scheduler=scheduler, stages=["vae_encoder", "unet", "vae"])
+        self.strict_schedule = False  # True: run all S evaluations (t_start = 0) instead of the reference's S - 1
+        self.sample_posterior = True  # the reference VAE-encoder engine samples its posterior (models.py:1334-1335)
+
+    # inpaint_pipeline.py:39-50. Settings arrive as numpy scalars from the wire header (server_io.py:105-119): cast first
+    # (numpy >= 2 overflows on 1000 // np.uint8(20) and wraps np.uint8(0) - 1). The reference
+    # crashes here for DDIM when `steps` changes (scheduler.beta_start is never stored); the evident intent is implemented.
+    def update_infer_settings(self, denoising_steps, guidance_scale, texture_guidance_scale, texture_guidance_steps):
+        self.guidance_scale = float(guidance_scale)
+        self.denoising_steps = int(denoising_steps)
+        self.texture_guidance_scale = float(texture_guidance_scale)
+        self.texture_guidance_steps = int(texture_guidance_steps)
+        if self.denoising_steps != self.scheduler.num_inference_steps:
+            self.scheduler.set_timesteps(self.denoising_steps)
+            self.scheduler.configure()
+
+    def _push_schedule(self, strength):
+        timesteps, t_start = self.initialize_timesteps(self.denoising_steps, strength)
+        if self.strict_schedule:
+            t_start = 0
+        key = (self.denoising_steps, t_start, self.guidance_scale, self.texture_guidance_scale,
+               self.texture_guidance_steps)
+        if key != self._schedule_key:
+            ts, at, ap = self.scheduler.evaluation_schedule(t_start)
+            self.engine.set_schedule(ts, at, ap, self.guidance_scale, self.texture_guidance_scale,
+                                     self.texture_guidance_steps)
+            self._schedule_key = key
+        return t_start
+
+    def set_condition(self, prompt, negative_prompt):
+        """text_embeddings = cat([negative, prompt, prompt]).half() (inpaint_pipeline.py:140); the cross-attention K/V of
+        all layers are projected once per brush instead of once per UNet call."""
+        self.engine.set_condition(prompt, negative_prompt)
+        self._cond_key = (prompt.data_ptr(), negative_prompt.data_ptr(), prompt._version, negative_prompt._version)
+
+    def infer(self, prompt, negative_prompt, input_image, mask_image, context_masked_image, context_mask, image_height,
+              image_width, seed=None, strength=1.0, verbose=False, init_latents=None, vae_noise=None):
+        """-> (B,3,H,W) float32 in [0,1] on the device. `seed` is ignored exactly as in the reference
+        (inpaint_pipeline.py:62); `init_latents` / `vae_noise` (extensions) make a run reproducible across devices."""
+        if image_height != image_width:
+            raise ValueError("square patches only")
+        B = input_image.shape[0]  # the reference derives it from the (1,14,768) prompt and only works for 1
+        h = image_height // 8
+        key = (prompt.data_ptr(), negative_prompt.data_ptr(), prompt._version, negative_prompt._version)
+        if getattr(self, "_cond_key", None) != key:
+            self.set_condition(prompt, negative_prompt)
+        if init_latents is None:
+            init_latents = self.initialize_latents(B, 4, h, h)
+        if vae_noise is None and self.sample_posterior:
+            vae_noise = torch.randn((2 * B, 4, h, h), device=self.device, dtype=torch.float32,
+                                    generator=self.noise_generator)
+        self._push_schedule(strength)
+        return self.engine.infer(input_image, mask_image, context_masked_image, context_mask, init_latents, vae_noise)

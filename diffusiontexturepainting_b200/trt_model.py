@@ -1,0 +1,148 @@
+"""Drop-in for trt_inference/trt_model.py: TRTConditionalInpainter with the reference's constructor, set_brush,
+generate_raw and (via the base class contract) generate — the surface trt_inference/handler.py drives
+(handler.py:66-110). No TensorRT anywhere: the name is kept so that `from trt_model import TRTConditionalInpainter`
+in run.py:21 keeps working."""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import _native as nat
+from . import weights as W
+from .image_encoder import ConditionPatchEncoder
+from .inpaint_pipeline import InpaintPipeline
+from .model_base import ConditionalInpainterBase
+
+
+def crop_resize_square(image, width):
+    """handler.py:36-45: CenterCrop(min side) then Resize(width) (bilinear; antialias off as in the reference container's
+    torchvision 0.15 tensor path)."""
+    H, W_ = image.shape[-2:]
+    m = min(H, W_)
+    if width is None or width <= 0:
+        width = m
+    top, left = int(round((H - m) / 2.0)), int(round((W_ - m) / 2.0))
+    img = image[..., top:top + m, left:left + m]
+    if m != width:
+        lead = img.dim() == 3
+        img = F.interpolate(img[None] if lead else img, size=(width, width), mode="bilinear", align_corners=False)
+        img = img[0] if lead else img
+    return img
+
+
+class TRTConditionalInpainter(ConditionalInpainterBase):
+    def __init__(self, resolution, device=0, model_config=None, state_dicts=None, max_batch_size=1, verbose=False):
+        super().__init__()
+        self.verbose = verbose
+        self.pipeline = InpaintPipeline(
+            scheduler="DDIM", guidance_scale=2, denoising_steps=20, texture_guidance_steps=20, version="1.5",
+            hf_token="", verbose=False, nvtx_profile=False, max_batch_size=16, device=device,
+            model_config=model_config, state_dicts=None)
+        cfg = self.pipeline.model_config
+        sds = state_dicts
+        if sds is None:
+            from .stable_diffusion_pipeline import load_state_dicts
+            sds = load_state_dicts(cfg, "/workspace/checkpoints/pytorch_lora_weights.bin")
+        self.pipeline._state_dicts = sds
+        self.pipeline.loadEngines("/workspace/engine", "/workspace/onnx", 16, opt_batch_size=max_batch_size,
+                                  opt_image_height=resolution, opt_image_width=resolution, text_maxlen=14,
+                                  lora_path="/workspace/checkpoints/pytorch_lora_weights.bin",
+                                  timing_cache="./timing.cache")
+        self.pipeline.loadResources(resolution, resolution, batch_size=1, seed=42)
+        self.image_encoder = ConditionPatchEncoder(self.pipeline.engine, cfg.enc.num_patches)
+        self.image_encoder.uncond_vector = sds[2]["uncond_vector"].float().to(self.pipeline.device)
+        self._resolution = resolution
+        self.conditioning = None
+        self.image = None
+        self._device = device
+
+    def device(self):
+        return self._device
+
+    def resolution(self):
+        return self._resolution
+
+    @property
+    def engine(self):
+        return self.pipeline.engine
+
+    def set_brush(self, image):
+        """image: 3 x H x W float32 0..1 (trt_model.py:79-88)."""
+        self.image = crop_resize_square(image, width=self.resolution()).unsqueeze(0).to(self.pipeline.device).float() \
+            .contiguous()
+        self.conditioning = self.image_encoder.encode_image(self.image)
+        self.pipeline.set_condition(*self.conditioning)
+
+    @staticmethod
+    def _settings(settings):
+        # wire values are numpy scalars (server_io.py:105-119)
+        return dict(steps=int(settings["steps"]), context_pad=int(settings["context_pad"]),
+                    tg_steps=int(settings["tg_steps"]), cfg_weight=float(settings["cfg_weight"]),
+                    tg_weight=float(settings["tg_weight"]))
+
+    def preprocess_canvas(self, canvas, pad):
+        """trt_model.py:103-109 + handler.py:25-33 in one pair of kernels (separable flat dilation)."""
+        B, _, R, _ = canvas.shape
+        dev = canvas.device
+        mi, ci = torch.empty(B, 3, R, R, device=dev), torch.empty(B, 3, R, R, device=dev)
+        m, cm = torch.empty(B, 1, R, R, device=dev), torch.empty(B, 1, R, R, device=dev)
+        scratch = torch.empty(B, R, R, device=dev)
+        nat.check_op(nat.lib().dtp_op_canvas_preprocess(nat.ptr(canvas), nat.ptr(self.image), B, R, int(pad),
+                                                        nat.ptr(mi), nat.ptr(m), nat.ptr(ci), nat.ptr(cm),
+                                                        nat.ptr(scratch), nat.stream_ptr()), "canvas_preprocess")
+        return mi, m, ci, cm
+
+    def generate_raw(self, canvas, init_latents=None, vae_noise=None, **settings):
+        """canvas: B x 4 x res x res float32 0..1 -> B x 3 x res x res float32 0..1 (trt_model.py:90-121)."""
+        if self.conditioning is None:
+            raise RuntimeError("set_brush must be called before generate")
+        s = self._settings(settings)
+        canvas = canvas.to(self.pipeline.device, torch.float32).contiguous()
+        masked_images, masks, context_masked_image, context_mask = self.preprocess_canvas(canvas, s["context_pad"])
+        self.pipeline.update_infer_settings(denoising_steps=s["steps"], guidance_scale=s["cfg_weight"],
+                                            texture_guidance_scale=s["tg_weight"],
+                                            texture_guidance_steps=s["tg_steps"])
+        start = time.time()
+        image_embeds, negative_embeds = self.conditioning
+        result = self.pipeline.infer(prompt=image_embeds, negative_prompt=negative_embeds, input_image=masked_images,
+                                     mask_image=masks, context_masked_image=context_masked_image,
+                                     context_mask=context_mask, image_width=self.resolution(),
+                                     image_height=self.resolution(), init_latents=init_latents, vae_noise=vae_noise)
+        if self.verbose:
+            torch.cuda.synchronize()
+            print("Inference time:", time.time() - start)
+        return result
+
+    def generate(self, canvas, init_latents=None, vae_noise=None, **settings):
+        """model_base.py:51-58 with the alpha composite as one kernel."""
+        canvas = canvas.to(self.pipeline.device, torch.float32).contiguous()
+        result = self.generate_raw(canvas, init_latents=init_latents, vae_noise=vae_noise, **settings)
+        B, _, R, _ = canvas.shape
+        out = torch.empty_like(result)
+        nat.check_op(nat.lib().dtp_op_composite(nat.ptr(canvas), nat.ptr(result), B, R, nat.ptr(out), None,
+                                                nat.stream_ptr()), "composite")
+        return out
+
+    def stamp_u8(self, canvas_u8_hwc, init_latents=None, vae_noise=None, **settings):
+        """Fast path for the websocket handler: uint8 HWC RGBA canvas (host or device) in, uint8 HWC RGB
+        stamp out, everything between in one dtp_stamp call (pre-process, infer, composite, x255 truncation)."""
+        s = self._settings(settings)
+        dev = self.pipeline.device
+        c = canvas_u8_hwc if torch.is_tensor(canvas_u8_hwc) else torch.from_numpy(canvas_u8_hwc)
+        if c.dim() == 3:
+            c = c.unsqueeze(0)
+        canvas = (c.to(dev, non_blocking=True).to(torch.float32).permute(0, 3, 1, 2) / 255).contiguous()
+        B, _, R, _ = canvas.shape
+        h = R // 8
+        self.pipeline.update_infer_settings(s["steps"], s["cfg_weight"], s["tg_weight"], s["tg_steps"])
+        self.pipeline._push_schedule(1.0)
+        if init_latents is None:
+            init_latents = self.pipeline.initialize_latents(B, 4, h, h)
+        if vae_noise is None and self.pipeline.sample_posterior:
+            vae_noise = torch.randn((2 * B, 4, h, h), device=dev, dtype=torch.float32,
+                                    generator=self.pipeline.noise_generator)
+        out = torch.empty(B, R, R, 3, device=dev, dtype=torch.uint8)
+        self.engine.stamp(canvas, self.image, s["context_pad"], init_latents, vae_noise, composite=True, out_u8=out)
+        return out

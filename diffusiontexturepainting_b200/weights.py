@@ -388,7 +388,8 @@ def pack_unet(unet_sd_merged: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor
             out[k] = v[perm].half().contiguous()
             bk = k[:-len("weight")] + "bias"
             out[bk] = sd[bk][perm].float().contiguous()
-            done.add(bk)
+        elif k.endswith("ff.net.0.proj.bias"):
+            continue
         elif v.dim() == 4 and v.shape[-1] == 3:
             out[k] = pack_conv3x3(v)
         elif v.dim() == 4:
@@ -411,6 +412,11 @@ def pack_vae(vae_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
                                              vae_sd[b + "value.bias"]], 0).float().contiguous()
         elif any(k.endswith(f".{n}.{t}") for n in ("query", "key", "value") for t in ("weight", "bias")):
             continue
+        elif k == "post_quant_conv.weight":
+            # 1x1 conv on the 4 latent channels; K padded to 8 so that activation rows are 16-byte aligned for TMA
+            t = torch.zeros(v.shape[0], 8, dtype=torch.float32)
+            t[:, :v.shape[1]] = v.reshape(v.shape[0], v.shape[1]).float()
+            out[k] = t.half().contiguous()
         elif v.dim() == 4 and v.shape[-1] == 3:
             out[k] = pack_conv3x3(v)
         elif v.dim() == 4:
@@ -420,6 +426,31 @@ def pack_vae(vae_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         else:
             out[k] = v.float().contiguous()
     return out
+
+
+def positional_encoding_2d(channels: int, height: int, width: int) -> torch.Tensor:
+    """2-D sinusoidal table of ConditionPatchEncoder (trt_inference/image_encoder.py:20-31): x on the first half of the
+    channels, y on the second half, sin on even / cos on odd channel indices."""
+    pe = torch.zeros(channels, height, width)
+    d = channels // 2
+    inv = torch.pow(10000.0, -torch.arange(0.0, d, 2) / d)
+    xs = torch.arange(0.0, width)[None, :] * inv[:, None]   # (d/2, W)
+    ys = torch.arange(0.0, height)[None, :] * inv[:, None]  # (d/2, H)
+    pe[0:d:2] = torch.sin(xs)[:, None, :].expand(-1, height, -1)
+    pe[1:d:2] = torch.cos(xs)[:, None, :].expand(-1, height, -1)
+    pe[d::2] = torch.sin(ys)[:, :, None].expand(-1, -1, width)
+    pe[d + 1::2] = torch.cos(ys)[:, :, None].expand(-1, -1, width)
+    return pe
+
+
+def patch_pos_emb(hid: int, num_patches=(1, 4, 9)) -> torch.Tensor:
+    """(1, 14, hid) table: each (C, s, s) grid is REINTERPRETED as (s*s, C) (a raw view, not a permute) exactly as the
+    reference does (image_encoder.py:54-56) — the model was trained with that scramble."""
+    parts = []
+    for n in num_patches:
+        s = int(round(n ** 0.5))
+        parts.append(positional_encoding_2d(hid, s, s).reshape(1, n, hid))
+    return torch.cat(parts, dim=1)
 
 
 def pack_encoder(enc_sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:

@@ -90,6 +90,72 @@ int dtp_op_canvas_preprocess(const float* canvas, const float* brush, int B, int
 int dtp_op_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * pipeline entry points
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct dtp_config {
+    /* UNet2DConditionModel (SD-1.5 inpainting: 9 in, 4 out, [320,640,1280,1280], 2 layers, 8 heads, ctx 768) */
+    int unet_in_channels, unet_out_channels;
+    int unet_block_out[4];
+    int unet_down_attn[4];
+    int unet_layers_per_block;
+    int unet_heads;
+    int unet_cross_dim;
+    int groups; /* GroupNorm groups (32) for UNet and VAE */
+    /* AutoencoderKL ([128,256,512,512], 2 layers, 4 latent channels) */
+    int vae_block_out[4];
+    int vae_layers_per_block;
+    int vae_latent;
+    /* ConditionPatchEncoder: CLIP ViT-B/32 visual (768, 12 layers, 12 heads, mlp 3072) + 3 towers of 4 blocks x 4 heads */
+    int enc_width, enc_layers, enc_heads, enc_mlp, enc_tower_layers, enc_tower_heads, enc_cross_dim;
+    int enc_tokens; /* 14 = 1 + 4 + 9 patches */
+    unsigned long long arena_bytes; /* transient activation slab; 0 = 8 GiB */
+} dtp_config;
+
+typedef struct dtp_engine dtp_handle;
+
+int dtp_create(const dtp_config* cfg, dtp_handle** out);
+void dtp_destroy(dtp_handle* h);
+const char* dtp_last_error(dtp_handle* h);
+
+/* Hand one named tensor (HOST memory, dtype 0 = f32, 1 = f16) to the engine; it is copied to the device. Names and layouts
+ * are those produced by diffusiontexturepainting_b200/weights.py pack_unet / pack_vae / pack_encoder with the prefixes
+ * "unet.", "vae.", "enc.". Replaces Engine.load + the ONNX/plan caches (stable_diffusion_pipeline.py:263-334). */
+int dtp_set_tensor(dtp_handle* h, const char* name, const void* host_ptr, const long long* shape, int ndim, int dtype);
+int dtp_finalize_weights(dtp_handle* h);
+
+/* ConditionPatchEncoder.forward (image_encoder.py:78-98): patches (14,3,224,224) f32 normalised -> emb (14, cross) f32 */
+int dtp_encode_patches(dtp_handle* h, const float* patches, float* emb_out, void* stream, void* reserved);
+/* text_embeddings = cat([negative, prompt, prompt]).half() (inpaint_pipeline.py:140) + cross-attention K/V of all
+ * transformer layers projected once for both embeddings. emb / uncond: (14, cross) f32. */
+int dtp_set_condition(dtp_handle* h, const float* emb, const float* uncond, void* stream);
+/* Explicit evaluation schedule (host arrays of length n): timestep, alpha_cumprod[t], alpha_cumprod[t_prev] per UNet
+ * evaluation; cfg / tg weights; tg is forced to 0 from evaluation index tg_steps on
+ * (stable_diffusion_pipeline.py:419-420). The reference's `steps = S` semantics (S-1 evaluations) is produced by the
+ * Python façade (inpaint_pipeline.py), a strict S-evaluation schedule by passing all S entries. */
+int dtp_set_schedule(dtp_handle* h, int n, const float* timesteps, const float* alpha_t, const float* alpha_prev,
+                     float cfg, float tg, int tg_steps);
+/* InpaintPipeline.infer: all tensors f32 NCHW on the device. masked_img/ctx_img (B,3,R,R) in [-1,1]; mask/ctx_mask
+ * (B,1,R,R) with 1 = generate; init_latents (B,4,R/8,R/8); vae_noise (2B,4,R/8,R/8) or NULL (posterior mode);
+ * out_images (B,3,R,R) in [0,1]. */
+int dtp_infer(dtp_handle* h, int B, int R, const float* masked_img, const float* mask, const float* ctx_img,
+              const float* ctx_mask, const float* init_latents, const float* vae_noise, float* out_images, void* stream);
+/* TRTConditionalInpainter.generate_raw (composite = 0) / ConditionalInpainterBase.generate (composite = 1):
+ * canvas (B,4,R,R) f32 0..1, brush (1,3,R,R) f32 0..1. out_f32 (B,3,R,R) and/or out_u8 (B,R,R,3), either nullable. */
+int dtp_stamp(dtp_handle* h, int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+              const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, void* stream);
+/* stage entry points (roofline isolation and per-stage parity) */
+int dtp_vae_encode(dtp_handle* h, int Nb, int R, const float* images, const float* noise, float* latents_out,
+                   void* stream); /* latents = 0.18215 * sample */
+int dtp_vae_decode(dtp_handle* h, int B, int R, const float* latents, float* images_out,
+                   void* stream); /* images = clamp(decode(latents / 0.18215)/2 + 0.5, 0, 1) */
+/* one UNet evaluation at schedule index `step`: sample (3B,9,h,h) f32 -> eps (3B,4,h,h) f32 */
+int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const float* reserved0, const float* reserved1,
+                     int step, float* eps_out, void* stream);
+/* counters: "launches" (kernels launched by this engine so far), "stamps", "arena_peak", "arena_bytes" */
+long long dtp_get_counter(dtp_handle* h, const char* name);
+int dtp_set_option(dtp_handle* h, const char* name, int value);
+
 #ifdef __cplusplus
 }
 #endif

