@@ -3,6 +3,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,10 +57,49 @@ void Arena::release(void* p) {
     free_[start] = sz;
 }
 
-int Plan::run(cudaStream_t st, long long* launch_counter) const {
-    for (const auto& op : ops) {
-        const int r = op(st);
+cudaEvent_t Profiler::get() {
+    if (next == pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+    }
+    return pool[next++];
+}
+void Profiler::collect() {
+    if (recs.empty()) return;
+    cudaEventSynchronize(recs.back().b);
+    for (auto& r : recs) {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        us[r.kind] += 1000.0 * ms;
+        n[r.kind] += r.launches;
+    }
+    recs.clear();
+    next = 0;
+}
+void Profiler::reset() {
+    collect();
+    for (int i = 0; i < K_NUM; ++i) {
+        us[i] = 0;
+        n[i] = 0;
+    }
+}
+
+int Plan::run(cudaStream_t st, long long* launch_counter, Profiler* prof) const {
+    const bool p = prof && prof->on;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        if (p) {
+            a = prof->get();
+            b = prof->get();
+            cudaEventRecord(a, st);
+        }
+        const int r = ops[i](st);
         if (r < 0) return r;
+        if (p) {
+            cudaEventRecord(b, st);
+            prof->recs.push_back({i < kinds.size() ? kinds[i] : 0, r, a, b});
+        }
         if (launch_counter) *launch_counter += r;
     }
     return 0;
@@ -153,7 +193,7 @@ struct Builder {
     void push_gemm(GemmOp op) {
         e.ws_needed_ = std::max(e.ws_needed_, gemm_workspace_bytes(&op));
         Engine* eng = &e;
-        plan.ops.push_back([op, eng](cudaStream_t st) mutable -> int {
+        plan.add(K_GEMM, [op, eng](cudaStream_t st) mutable -> int {
             op.p.workspace = eng->ws_;
             if (gemm_launch(&op, st)) {
                 eng->err_ = std::string("contraction launch failed: ") + gemm_last_error();
@@ -243,7 +283,7 @@ struct Builder {
         const __half *x0 = a0.p, *x1 = a1.p;
         const int C0 = a0.C, C1 = a1.p ? a1.C : 0, Nimg = a0.N;
         __half* o = out.p;
-        plan.ops.push_back([=](cudaStream_t st) -> int {
+        plan.add(K_GROUPNORM, [=](cudaStream_t st) -> int {
             if (launch_groupnorm(x0, C0, x1, C1, Nimg, HW, groups, g, bt, eps, silu, o, ws, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -262,7 +302,7 @@ struct Builder {
         Engine* eng = &e;
         const __half* xp = x.p;
         const int rows = static_cast<int>(x.rows()), C = x.C;
-        plan.ops.push_back([=](cudaStream_t st) -> int {
+        plan.add(K_LAYERNORM, [=](cudaStream_t st) -> int {
             if (launch_layernorm(xp, rows, C, g, bt, 1e-5f, out, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -279,7 +319,7 @@ struct Builder {
         Engine* eng = &e;
         const float scale = 1.0f / sqrtf(static_cast<float>(d));
         if (nkv <= 64) {
-            plan.ops.push_back([=](cudaStream_t st) -> int {
+            plan.add(K_ATTN_SMALL, [=](cudaStream_t st) -> int {
                 if (launch_attn_small(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, heads, d, batch, q_bs, kv_bs, o_bs,
                                       kv_index, scale, st)) {
                     eng->err_ = kernels_last_error();
@@ -312,7 +352,7 @@ struct Builder {
         qk.p.out_zs2 = static_cast<long long>(heads) * nq * ldS;
         qk.p.alpha = scale;
         push_gemm(qk);
-        plan.ops.push_back([=](cudaStream_t st) -> int {
+        plan.add(K_SOFTMAX, [=](cudaStream_t st) -> int {
             if (launch_softmax_rows(S, srows, nkv, ldS, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -341,7 +381,7 @@ struct Builder {
         const __half* xp = x.p;
         __half* o = out.p;
         const int N = x.N, H = x.H, W = x.W, C = x.C;
-        plan.ops.push_back([=](cudaStream_t st) -> int {
+        plan.add(K_OTHER, [=](cudaStream_t st) -> int {
             if (launch_upsample2x(xp, N, H, W, C, o, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -367,7 +407,7 @@ struct Builder {
         const __half* xp = x.p;
         __half* cp = col.p;
         const int N = x.N, H = x.H, Wd = x.W, C = x.C;
-        plan.ops.push_back([=](cudaStream_t st) -> int {
+        plan.add(K_OTHER, [=](cudaStream_t st) -> int {
             if (launch_im2col_s2(xp, N, H, Wd, C, pad_lo, Ho, Wo, cp, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -498,12 +538,13 @@ int Engine::set_tensor(const char* name, const void* host, const int64_t* shape,
     const size_t bytes = static_cast<size_t>(t.numel()) * (dtype == 0 ? 4 : 2);
     if (cudaMalloc(&t.dev, bytes ? bytes : 16) != cudaSuccess)
         return fail(std::string("set_tensor: cudaMalloc failed for ") + name);
-    if (cudaMemcpy(t.dev, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMemcpy(t.dev, host, bytes, cudaMemcpyDefault) != cudaSuccess) {
         cudaFree(t.dev);
         return fail(std::string("set_tensor: copy failed for ") + name);
     }
     if (dtype == 0 && t.numel() <= (1 << 22)) {
-        t.host.assign(static_cast<const float*>(host), static_cast<const float*>(host) + t.numel());
+        t.host.resize(t.numel());
+        cudaMemcpy(t.host.data(), host, bytes, cudaMemcpyDefault);  // host or device source (UVA)
     }
     auto it = w_.find(name);
     if (it != w_.end()) {
@@ -727,7 +768,7 @@ int Engine::build_unet_plan(int B, int R) {
     arena_.reset();
     Builder b(*this, unet_plan_, "unet.");
     // op 0: select the time-embedding bias row of the step being evaluated
-    unet_plan_.ops.push_back([this](cudaStream_t st) -> int {
+    unet_plan_.add(K_OTHER, [this](cudaStream_t st) -> int {
         if (launch_copy_f32(temb_all_ + static_cast<size_t>(cur_step_) * temb_total_, temb_cur_, temb_total_, st)) {
             err_ = kernels_last_error();
             return -1;
@@ -989,7 +1030,7 @@ int Engine::build_encoder_plan() {
     if (b.ok) {
         const float* src = enc_in_copy_;
         __half* dst = pat.p;
-        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+        enc_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
             if (launch_patchify32(src, T, dst, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -1011,7 +1052,7 @@ int Engine::build_encoder_plan() {
         const float* pos = b.F32(v + ".positional_embedding");
         const __half* tp = tok.p;
         __half* xp = x.p;
-        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+        enc_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
             if (launch_clip_embed(tp, cls, pos, T, w, xp, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -1079,7 +1120,7 @@ int Engine::build_encoder_plan() {
         cudaMemcpy(didx, idx.data(), T * sizeof(int), cudaMemcpyHostToDevice);
         const __half* xp = x.p;
         __half* cp = cls.p;
-        enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+        enc_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
             if (launch_gather_rows(xp, w, didx, T, w, cp, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
@@ -1090,7 +1131,7 @@ int Engine::build_encoder_plan() {
         const float* pe = b.F32("pos_emb");
         __half* lp = lat.p;
         if (b.ok)
-            enc_plan_.ops.push_back([=](cudaStream_t st) -> int {
+            enc_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
                 if (launch_add_rows_bcast(lp, pe, T, w, T, st)) {
                     eng->err_ = kernels_last_error();
                     return -1;
@@ -1177,7 +1218,7 @@ int Engine::encode_patches(const float* patches, float* emb_out, cudaStream_t st
     const size_t n = static_cast<size_t>(cfg_.enc_tokens) * 3 * 224 * 224;
     if (cudaMemcpyAsync(enc_in_copy_, patches, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         return fail("encode_patches: input copy failed");
-    if (enc_plan_.run(st, &launches_)) return -1;
+    if (enc_plan_.run(st, &launches_, &prof_)) return -1;
     if (cudaMemcpyAsync(emb_out, enc_out_, static_cast<size_t>(cfg_.enc_tokens) * cfg_.enc_cross_dim * 4,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         return fail("encode_patches: output copy failed");
@@ -1193,7 +1234,7 @@ int Engine::build_cond_plan() {
     Builder b(*this, cond_plan_, "unet.");
     const int T = cfg_.enc_tokens, D = cfg_.unet_cross_dim;
     Engine* eng = this;
-    cond_plan_.ops.push_back([=](cudaStream_t st) -> int {
+    cond_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
         if (launch_f32_to_f16(eng->ctx_f32_, eng->ctx_, static_cast<long long>(2) * T * D, st)) {
             eng->err_ = kernels_last_error();
             return -1;
@@ -1224,7 +1265,7 @@ int Engine::set_condition(const float* emb, const float* uncond, cudaStream_t st
     if (cudaMemcpyAsync(ctx_f32_, uncond, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(ctx_f32_ + n, emb, n * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
         return fail("set_condition: copy failed");
-    if (cond_plan_.run(st, &launches_)) return -1;
+    if (cond_plan_.run(st, &launches_, &prof_)) return -1;
     cond_set_ = true;
     return 0;
 }
@@ -1271,7 +1312,7 @@ int Engine::build_temb_tables(cudaStream_t st) {
     Plan p;
     Builder b(*this, p, "unet.");
     Engine* eng = this;
-    p.ops.push_back([=](cudaStream_t s) -> int {
+    p.add(K_OTHER, [=](cudaStream_t s) -> int {
         if (launch_timestep_embedding(d_ts, n, c0, e16, s)) {
             eng->err_ = kernels_last_error();
             return -1;
@@ -1305,7 +1346,7 @@ int Engine::build_temb_tables(cudaStream_t st) {
     }
     int rc = b.ok ? 0 : -1;
     if (rc == 0) rc = ensure_ws();
-    if (rc == 0) rc = p.run(st, &launches_);
+    if (rc == 0) rc = p.run(st, &launches_, &prof_);
     cudaStreamSynchronize(st);
     cudaFree(d_ts);
     cudaFree(e16);
@@ -1332,7 +1373,7 @@ int Engine::vae_encode(int Nb, int R, const float* images, const float* noise, f
     if (build_vae_enc_plan(Nb, R)) return -1;
     const int h = R / 8;
     KCHECK(launch_nchw_to_nhwc_pad(images, Nb, 3, R * R, 64, 1.0f, vae_enc_in_, st));
-    if (vae_enc_plan_.run(st, &launches_)) return -1;
+    if (vae_enc_plan_.run(st, &launches_, &prof_)) return -1;
     KCHECK(launch_vae_sample(vae_moments_, noise, Nb, h * h, 0.18215f, latents_out, st));
     return 0;
 }
@@ -1342,7 +1383,7 @@ int Engine::vae_decode(int B, int R, const float* latents, float* images_out, cu
     if (build_vae_dec_plan(B, R)) return -1;
     const int h = R / 8;
     KCHECK(launch_nchw_to_nhwc_pad(latents, B, cfg_.vae_latent, h * h, 8, 0.18215f, vae_dec_in_, st));
-    if (vae_dec_plan_.run(st, &launches_)) return -1;
+    if (vae_dec_plan_.run(st, &launches_, &prof_)) return -1;
     if (images_out != vae_dec_out_)
         KCHECK(launch_copy_f32(vae_dec_out_, images_out, static_cast<long long>(B) * 3 * R * R, st));
     return 0;
@@ -1362,7 +1403,7 @@ int Engine::unet_forward(int B, int R, const float* sample, const float* latents
         KCHECK(launch_pack_unet_input(latents, mask3, masked3, B, h * h, unet_in_, st));
     }
     cur_step_ = step;
-    if (unet_plan_.run(st, &launches_)) return -1;
+    if (unet_plan_.run(st, &launches_, &prof_)) return -1;
     if (eps_out && eps_out != unet_eps_)
         KCHECK(launch_copy_f32(unet_eps_, eps_out, static_cast<long long>(Bz) * cfg_.unet_out_channels * h * h, st));
     return 0;
@@ -1454,6 +1495,13 @@ long long Engine::counter(const char* name) const {
     if (n == "arena_bytes") return static_cast<long long>(cfg_.arena_bytes);
     if (n == "unet_plan_ops") return static_cast<long long>(unet_plan_.ops.size());
     if (n == "ws_bytes") return static_cast<long long>(ws_bytes_);
+    if (n.rfind("prof_us_", 0) == 0 || n.rfind("prof_n_", 0) == 0) {
+        const_cast<Profiler&>(prof_).collect();
+        const bool is_us = n[5] == 'u';
+        const int k = atoi(n.c_str() + (is_us ? 8 : 7));
+        if (k < 0 || k >= K_NUM) return -1;
+        return is_us ? static_cast<long long>(prof_.us[k]) : prof_.n[k];
+    }
     return -1;
 }
 
@@ -1461,6 +1509,11 @@ int Engine::set_option(const char* name, int value) {
     const std::string n = name ? name : "";
     if (n == "sync_check") {
         opt_sync_check_ = value;
+        return 0;
+    }
+    if (n == "profile") {
+        prof_.reset();
+        prof_.on = value != 0;
         return 0;
     }
     return fail("unknown option " + n);

@@ -61,12 +61,38 @@ struct Act {  // NHWC fp16 activation: rows = N*H*W pixels, C channels
     size_t bytes() const { return static_cast<size_t>(rows()) * C * sizeof(__half); }
 };
 
+enum OpKind { K_OTHER = 0, K_GEMM = 1, K_GROUPNORM = 2, K_LAYERNORM = 3, K_SOFTMAX = 4, K_ATTN_SMALL = 5, K_NUM = 6 };
+
+// Optional per-op device timing (CUDA events on the launching stream), enabled with dtp_set_option("profile", 1).
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    struct Rec {
+        int kind;
+        int launches;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+    size_t next = 0;
+    double us[K_NUM] = {0};
+    long long n[K_NUM] = {0};
+    cudaEvent_t get();
+    void collect();
+    void reset();
+};
+
 struct Plan {
     std::vector<std::function<int(cudaStream_t)>> ops;
+    std::vector<int> kinds;
     int key_a = -1, key_b = -1;  // (batch, resolution) the plan was built for
-    int run(cudaStream_t st, long long* launch_counter) const;
+    int run(cudaStream_t st, long long* launch_counter, Profiler* prof = nullptr) const;
+    void add(int kind, std::function<int(cudaStream_t)> f) {
+        ops.push_back(std::move(f));
+        kinds.push_back(kind);
+    }
     void clear() {
         ops.clear();
+        kinds.clear();
         key_a = key_b = -1;
     }
 };
@@ -162,6 +188,7 @@ class Engine {
     bool temb_dirty_ = true;
 
     long long launches_ = 0, stamps_ = 0;
+    Profiler prof_;
     int opt_sync_check_ = 0;
 };
 

@@ -81,7 +81,7 @@ class Engine:
     # ------------------------------------------------------------------ weights
     def load_packed(self, prefix: str, packed: Dict[str, torch.Tensor]):
         for name, t in packed.items():
-            t = t.detach().cpu().contiguous()
+            t = t.detach().contiguous()  # host or device memory: the engine copies with cudaMemcpyDefault
             if t.dtype == torch.float16:
                 dt = 1
             elif t.dtype == torch.float32:
@@ -101,6 +101,11 @@ class Engine:
         enc = W.pack_encoder(enc_sd)
         enc["pos_emb"] = W.patch_pos_emb(self.cfg.enc.width, self.cfg.enc.num_patches).reshape(-1, self.cfg.enc.width)
         self.load_packed("enc.", enc)
+        self._check(self._lib.dtp_finalize_weights(self._h), "dtp_finalize_weights")
+
+    def load_prepacked(self, packed: Dict[str, torch.Tensor]):
+        """Already packed + prefixed tensors (e.g. received through parallel.broadcast_packed)."""
+        self.load_packed("", packed)
         self._check(self._lib.dtp_finalize_weights(self._h), "dtp_finalize_weights")
 
     # ------------------------------------------------------------------ per brush
@@ -183,6 +188,15 @@ class Engine:
 
     def counter(self, name: str) -> int:
         return int(self._lib.dtp_get_counter(self._h, name.encode()))
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.dtp_set_option(self._h, name.encode(), int(value)), f"dtp_set_option({name})")
+
+    KINDS = ("other", "contraction", "groupnorm", "layernorm", "softmax", "attn_small")
+
+    def profile(self):
+        """{kind: (device microseconds, launches)} accumulated since set_option('profile', 1)."""
+        return {k: (self.counter(f"prof_us_{i}"), self.counter(f"prof_n_{i}")) for i, k in enumerate(self.KINDS)}
 
 
 def arena_estimate(cfg: W.ModelConfig, batch: int, resolution: int) -> int:

@@ -50,6 +50,10 @@ class StableDiffusionPipeline:
         arena = arena_estimate(self.model_config, max(1, opt_batch_size), max(opt_image_height, opt_image_width))
         arena = int(os.environ.get("DTP_ARENA_BYTES", arena))
         self.engine = Engine(self.model_config, dev_index, arena_bytes=arena)
+        if getattr(self, "_prepacked", None) is not None:
+            self.engine.load_prepacked(self._prepacked)
+            self._prepacked = None
+            return
         sds = self._state_dicts or load_state_dicts(self.model_config, lora_path, self._weight_seed)
         self.engine.load_state_dicts(*sds)
         self._state_dicts = None

@@ -33,7 +33,8 @@ def crop_resize_square(image, width):
 
 
 class TRTConditionalInpainter(ConditionalInpainterBase):
-    def __init__(self, resolution, device=0, model_config=None, state_dicts=None, max_batch_size=1, verbose=False):
+    def __init__(self, resolution, device=0, model_config=None, state_dicts=None, max_batch_size=1, verbose=False,
+                 preloaded=None):
         super().__init__()
         self.verbose = verbose
         self.pipeline = InpaintPipeline(
@@ -42,17 +43,22 @@ class TRTConditionalInpainter(ConditionalInpainterBase):
             model_config=model_config, state_dicts=None)
         cfg = self.pipeline.model_config
         sds = state_dicts
-        if sds is None:
-            from .stable_diffusion_pipeline import load_state_dicts
-            sds = load_state_dicts(cfg, "/workspace/checkpoints/pytorch_lora_weights.bin")
-        self.pipeline._state_dicts = sds
+        uncond = None
+        if preloaded is not None:  # (packed + prefixed tensor dict, uncond_vector): multi-GPU broadcast path
+            self.pipeline._prepacked, uncond = preloaded
+        else:
+            if sds is None:
+                from .stable_diffusion_pipeline import load_state_dicts
+                sds = load_state_dicts(cfg, "/workspace/checkpoints/pytorch_lora_weights.bin")
+            self.pipeline._state_dicts = sds
+            uncond = sds[2]["uncond_vector"]
         self.pipeline.loadEngines("/workspace/engine", "/workspace/onnx", 16, opt_batch_size=max_batch_size,
                                   opt_image_height=resolution, opt_image_width=resolution, text_maxlen=14,
                                   lora_path="/workspace/checkpoints/pytorch_lora_weights.bin",
                                   timing_cache="./timing.cache")
         self.pipeline.loadResources(resolution, resolution, batch_size=1, seed=42)
         self.image_encoder = ConditionPatchEncoder(self.pipeline.engine, cfg.enc.num_patches)
-        self.image_encoder.uncond_vector = sds[2]["uncond_vector"].float().to(self.pipeline.device)
+        self.image_encoder.uncond_vector = uncond.float().to(self.pipeline.device)
         self._resolution = resolution
         self.conditioning = None
         self.image = None

@@ -118,7 +118,7 @@ int dtp_create(const dtp_config* cfg, dtp_handle** out);
 void dtp_destroy(dtp_handle* h);
 const char* dtp_last_error(dtp_handle* h);
 
-/* Hand one named tensor (HOST memory, dtype 0 = f32, 1 = f16) to the engine; it is copied to the device. Names and layouts
+/* Hand one named tensor (host OR device memory, dtype 0 = f32, 1 = f16) to the engine; it is copied (cudaMemcpyDefault). Names and layouts
  * are those produced by diffusiontexturepainting_b200/weights.py pack_unet / pack_vae / pack_encoder with the prefixes
  * "unet.", "vae.", "enc.". Replaces Engine.load + the ONNX/plan caches (stable_diffusion_pipeline.py:263-334). */
 int dtp_set_tensor(dtp_handle* h, const char* name, const void* host_ptr, const long long* shape, int ndim, int dtype);
