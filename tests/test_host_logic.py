@@ -1,0 +1,149 @@
+"""CPU: host-side logic of the product (weight inventory, LoRA merge, packing layouts, schedule tables, façade plumbing)
+and the C-ABI surface (library loads and exports every symbol include/dtp.h declares; no compute calls without a GPU)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from diffusiontexturepainting_b200 import weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parameter_counts_match_sd15():
+    cfg = W.sd15_config()
+    n_unet = sum(math.prod(s) for k, s in W.unet_param_shapes(cfg.unet).items() if "lora" not in k)
+    n_vae = sum(math.prod(s) for s in W.vae_param_shapes(cfg.vae).values())
+    n_clip = sum(math.prod(s) for k, s in W.encoder_param_shapes(cfg.enc).items() if k.startswith("clip."))
+    assert n_unet == 859_535_364  # SD-1.5 inpainting UNet (9 input channels)
+    assert n_vae == 83_653_863
+    assert n_clip == 87_456_000  # ViT-B/32 visual tower without the projection
+    n_lora = sum(1 for k in W.unet_param_shapes(cfg.unet) if k.endswith("_lora.down.weight"))
+    assert n_lora == 32 * 4  # 32 attention modules x (q, k, v, out): train_texture_inpaint_lora.py:411-433
+
+
+def test_lora_merge_equals_residual():
+    from oracle import unet as un
+    cfg = W.tiny_config()
+    u = W.synth_state_dict(W.unet_param_shapes(cfg.unet), 3)
+    m = W.merge_lora(u)
+    assert not any(".processor." in k for k in m)
+    g = torch.Generator().manual_seed(0)
+    x, ctx = torch.randn(3, 9, 8, 8, generator=g), torch.randn(3, 14, cfg.unet.cross_dim, generator=g)
+    a = un.unet_forward(u, cfg.unet, x, 501, ctx)
+    b = un.unet_forward(m, cfg.unet, x, 501, ctx)
+    assert torch.allclose(a, b, atol=2e-5)
+    k = "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k"
+    d = m[k + ".weight"] - u[k + ".weight"]
+    lo = u[k.replace(".to_k", ".processor.to_k_lora.up.weight")] @ u[k.replace(".to_k", ".processor.to_k_lora.down.weight")]
+    assert torch.allclose(d, lo, atol=1e-6) and d.abs().max() > 0
+
+
+def test_packing_layouts():
+    cfg = W.tiny_config()
+    u, v, e = W.synth_model(cfg, 5)
+    pu = W.pack_unet(W.merge_lora(u))
+    # conv3x3: [Cout, 9*Cin_pad], k = (ky*3+kx)*Cin_pad + c, zero padded channels
+    w = u["conv_in.weight"]
+    p = pu["conv_in.weight"].float().view(w.shape[0], 3, 3, 64)
+    assert torch.equal(p[..., :9], w.half().float().permute(0, 2, 3, 1)) and p[..., 9:].abs().max() == 0
+    # fused QKV / KV
+    b = "down_blocks.1.attentions.0.transformer_blocks.0"
+    C = cfg.unet.block_out_channels[1]
+    assert pu[f"{b}.attn1.to_qkv.weight"].shape == (3 * C, C)
+    assert pu[f"{b}.attn2.to_kv.weight"].shape == (2 * C, cfg.unet.cross_dim)
+    # GEGLU interleave: chunk of 32 rows = 16 value rows + their 16 gate rows
+    wf = W.merge_lora(u)[f"{b}.ff.net.0.proj.weight"].half()
+    pf = pu[f"{b}.ff.net.0.proj.weight"]
+    assert torch.equal(pf[0:16], wf[0:16]) and torch.equal(pf[16:32], wf[4 * C:4 * C + 16])
+    assert torch.equal(pf[32:48], wf[16:32])
+    bf = u[f"{b}.ff.net.0.proj.bias"]
+    assert torch.equal(pu[f"{b}.ff.net.0.proj.bias"][16:32], bf[4 * C:4 * C + 16])
+    assert all(t.dtype in (torch.float16, torch.float32) for t in pu.values())
+    assert not any(k.endswith((".to_k.weight", ".to_v.weight")) for k in pu)
+    pv = W.pack_vae(v)
+    assert pv["post_quant_conv.weight"].shape == (4, 8) and pv["post_quant_conv.weight"][:, 4:].abs().max() == 0
+    assert pv["encoder.mid_block.attentions.0.qkv.weight"].shape[0] == 3 * cfg.vae.block_out_channels[-1]
+    pe = W.pack_encoder(e)
+    assert pe["clip.visual.conv1.weight"].shape == (cfg.enc.width, 3072)
+    assert pe["l_patch_encoder_layers.0.attn1.to_qkv.bias"].shape == (3 * cfg.enc.width,)
+    assert pe["uncond_vector"].dtype == torch.float32
+
+
+def test_round_fp16_only_touches_matrices():
+    cfg = W.tiny_config()
+    u = W.synth_state_dict(W.unet_param_shapes(cfg.unet), 1)
+    r = W.round_fp16(u)
+    assert torch.equal(r["conv_in.bias"], u["conv_in.bias"])
+    assert torch.equal(r["conv_in.weight"], u["conv_in.weight"].half().float())
+
+
+def test_facade_settings_are_cast_from_numpy_scalars():
+    """Wire settings are numpy scalars (server_io.py:105-119); with numpy >= 2 `1000 // np.uint8(20)` overflows and
+    `np.uint8(0) - 1` wraps, so the façade casts on entry."""
+    from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
+    s = TRTConditionalInpainter._settings(dict(steps=np.uint8(20), context_pad=np.uint8(150), tg_steps=np.uint8(0),
+                                               width=np.uint16(256), cfg_weight=np.float32(2.0),
+                                               tg_weight=np.float32(1.0)))
+    assert s == dict(steps=20, context_pad=150, tg_steps=0, cfg_weight=2.0, tg_weight=1.0)
+    assert all(type(v) in (int, float) for v in s.values())
+    from diffusiontexturepainting_b200.scheduler import DDIMScheduler
+    d = DDIMScheduler(device="cpu")
+    d.set_timesteps(np.uint8(20))
+    d.configure()
+    assert int(d.timesteps[0]) == 951 and len(d.evaluation_schedule(1)[0]) == 19
+
+
+def test_crop_resize_square_and_patches():
+    from diffusiontexturepainting_b200.trt_model import crop_resize_square
+    from oracle import image_encoder as ie
+    img = torch.rand(3, 90, 130, generator=torch.Generator().manual_seed(0))
+    a = crop_resize_square(img, 64)
+    assert a.shape == (3, 64, 64) and torch.equal(a, ie.crop_resize_square(img, 64))
+    assert torch.equal(crop_resize_square(img[:, :64, :64], 64), img[:, :64, :64])
+
+
+def test_shard_range_partitions():
+    from diffusiontexturepainting_b200.parallel import shard_range
+    for n in (1, 7, 8, 32, 33):
+        for w in (1, 2, 4, 8):
+            parts = [shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+
+
+def test_library_exports_every_declared_symbol():
+    from diffusiontexturepainting_b200 import _native as nat
+    from diffusiontexturepainting_b200 import build
+    lib_path = build.build()
+    L = ctypes.CDLL(lib_path)
+    header = open(os.path.join(ROOT, "include", "dtp.h")).read()
+    declared = set(re.findall(r"\b(dtp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dtp_engine"}
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/dtp.h but not exported"
+    for name in nat.exported_symbols():
+        assert name in declared, f"{name} bound in _native.py but not declared in include/dtp.h"
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from diffusiontexturepainting_b200 import _native as nat
+    from diffusiontexturepainting_b200.engine import Engine
+    with pytest.raises(nat.DtpError):
+        Engine(W.tiny_config())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "diffusiontexturepainting_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
