@@ -45,6 +45,7 @@ _PIPE = {
     "dtp_unet_forward": [vp, i32, i32, vp, vp, vp, i32, vp, vp],
     "dtp_get_counter": [vp, cp],
     "dtp_set_option": [vp, cp, i32],
+    "dtp_profile_dump": [vp, cp],
 }
 
 

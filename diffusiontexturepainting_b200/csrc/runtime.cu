@@ -73,6 +73,11 @@ void Profiler::collect() {
         cudaEventElapsedTime(&ms, r.a, r.b);
         us[r.kind] += 1000.0 * ms;
         n[r.kind] += r.launches;
+        if (r.label && !r.label->empty()) {
+            auto& e = by_label[*r.label];
+            e.first += 1000.0 * ms;
+            e.second += 1;
+        }
     }
     recs.clear();
     next = 0;
@@ -83,6 +88,7 @@ void Profiler::reset() {
         us[i] = 0;
         n[i] = 0;
     }
+    by_label.clear();
 }
 
 int Plan::run(cudaStream_t st, long long* launch_counter, Profiler* prof) const {
@@ -98,7 +104,7 @@ int Plan::run(cudaStream_t st, long long* launch_counter, Profiler* prof) const 
         if (r < 0) return r;
         if (p) {
             cudaEventRecord(b, st);
-            prof->recs.push_back({i < kinds.size() ? kinds[i] : 0, r, a, b});
+            prof->recs.push_back({i < kinds.size() ? kinds[i] : 0, r, a, b, i < labels.size() ? &labels[i] : nullptr});
         }
         if (launch_counter) *launch_counter += r;
     }
@@ -190,9 +196,14 @@ struct Builder {
     }
     void release_raw(void* p) { e.arena_.release(p); }
 
-    void push_gemm(GemmOp op) {
+    void push_gemm(GemmOp op, const char* what = "linear") {
         e.ws_needed_ = std::max(e.ws_needed_, gemm_workspace_bytes(&op));
         Engine* eng = &e;
+        char lab[192];
+        snprintf(lab, sizeof(lab), "%s M=%d N=%d K=%d z=%d BN=%d splits=%d grid=%dx%d flags=0x%x", what, op.p.M, op.p.N,
+                 op.p.num_kb * 64, op.p.nz1 * op.p.nz2, op.BN, op.p.splits, op.grid_m, (op.p.N + op.BN - 1) / op.BN,
+                 op.p.flags);
+        const std::string label = lab;
         plan.add(K_GEMM, [op, eng](cudaStream_t st) mutable -> int {
             op.p.workspace = eng->ws_;
             if (gemm_launch(&op, st)) {
@@ -200,7 +211,7 @@ struct Builder {
                 return -1;
             }
             return op.p.splits > 1 ? 2 : 1;
-        });
+        }, label);
     }
 
     void linear(const Lin& a) {
@@ -256,7 +267,7 @@ struct Builder {
         op.p.ldc = ldc > 0 ? ldc : cout;
         op.p.flags |= flags;
         op.p.hw_out = hw_out;
-        push_gemm(op);
+        push_gemm(op, "conv3x3");
     }
     Act conv3x3(const Act& a0, const Act& a1, const std::string& p, const float* bias_override, const __half* res) {
         int cout = 0;
@@ -289,7 +300,7 @@ struct Builder {
                 return -1;
             }
             return 3;
-        });
+        }, "groupnorm rows=" + std::to_string(static_cast<long long>(Nimg) * HW) + " C=" + std::to_string(C0 + C1));
         release_raw(ws);  // stream-ordered: the next consumer of this slab runs after the norm
         return out;
     }
@@ -326,7 +337,8 @@ struct Builder {
                     return -1;
                 }
                 return 1;
-            });
+            }, "attn_small nq=" + std::to_string(nq) + " nkv=" + std::to_string(nkv) + " heads=" + std::to_string(heads) +
+                   " d=" + std::to_string(d) + " batch=" + std::to_string(batch));
             return;
         }
         if (kv_index) {
@@ -351,14 +363,14 @@ struct Builder {
         qk.p.out_zs1 = static_cast<long long>(nq) * ldS;
         qk.p.out_zs2 = static_cast<long long>(heads) * nq * ldS;
         qk.p.alpha = scale;
-        push_gemm(qk);
+        push_gemm(qk, "attn_qk");
         plan.add(K_SOFTMAX, [=](cudaStream_t st) -> int {
             if (launch_softmax_rows(S, srows, nkv, ldS, st)) {
                 eng->err_ = kernels_last_error();
                 return -1;
             }
             return 1;
-        });
+        }, "softmax rows=" + std::to_string(srows) + " cols=" + std::to_string(nkv));
         gemm_pick_config(mt, d, (nkv + 63) / 64, GEMM_B_MN, &BN, &sp);
         if (gemm_setup_batched(&pv, S, ldS, static_cast<long long>(nq) * ldS, static_cast<long long>(heads) * nq * ldS,
                                v, ldv, d, kv_bs, 1, nq, d, nkv, heads, batch, BN)) {
@@ -369,7 +381,7 @@ struct Builder {
         pv.p.ldc = ldo;
         pv.p.out_zs1 = d;
         pv.p.out_zs2 = o_bs;
-        push_gemm(pv);
+        push_gemm(pv, "attn_pv");
         release_raw(S);
     }
 
@@ -1505,6 +1517,20 @@ long long Engine::counter(const char* name) const {
     return -1;
 }
 
+int Engine::profile_dump(const char* path) {
+    prof_.collect();
+    FILE* f = fopen(path, "w");
+    if (!f) return fail(std::string("profile_dump: cannot open ") + path);
+    std::vector<std::pair<std::string, std::pair<double, long long>>> v(prof_.by_label.begin(), prof_.by_label.end());
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.second.first > b.second.first; });
+    fprintf(f, "total_us,calls,avg_us,op\n");
+    for (auto& e : v)
+        fprintf(f, "%.1f,%lld,%.2f,%s\n", e.second.first, e.second.second, e.second.first / e.second.second,
+                e.first.c_str());
+    fclose(f);
+    return 0;
+}
+
 int Engine::set_option(const char* name, int value) {
     const std::string n = name ? name : "";
     if (n == "sync_check") {
@@ -1594,5 +1620,6 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
 }
 long long dtp_get_counter(dtp_handle* h, const char* name) { return h->e->counter(name); }
 int dtp_set_option(dtp_handle* h, const char* name, int value) { return h->e->set_option(name, value); }
+int dtp_profile_dump(dtp_handle* h, const char* path) { return h->e->profile_dump(path); }
 
 }  // extern "C"

@@ -71,7 +71,9 @@ struct Profiler {
         int kind;
         int launches;
         cudaEvent_t a, b;
+        const std::string* label;
     };
+    std::map<std::string, std::pair<double, long long>> by_label;  // label -> (us, calls)
     std::vector<Rec> recs;
     size_t next = 0;
     double us[K_NUM] = {0};
@@ -84,15 +86,18 @@ struct Profiler {
 struct Plan {
     std::vector<std::function<int(cudaStream_t)>> ops;
     std::vector<int> kinds;
+    std::vector<std::string> labels;
     int key_a = -1, key_b = -1;  // (batch, resolution) the plan was built for
     int run(cudaStream_t st, long long* launch_counter, Profiler* prof = nullptr) const;
-    void add(int kind, std::function<int(cudaStream_t)> f) {
+    void add(int kind, std::function<int(cudaStream_t)> f, const std::string& label = std::string()) {
         ops.push_back(std::move(f));
         kinds.push_back(kind);
+        labels.push_back(label);
     }
     void clear() {
         ops.clear();
         kinds.clear();
+        labels.clear();
         key_a = key_b = -1;
     }
 };
@@ -117,6 +122,7 @@ class Engine {
                      int step, float* eps_out, cudaStream_t st);
     long long counter(const char* name) const;
     int set_option(const char* name, int value);
+    int profile_dump(const char* path);
     const char* last_error() const { return err_.c_str(); }
 
    private:

@@ -192,6 +192,9 @@ class Engine:
     def set_option(self, name: str, value: int):
         self._check(self._lib.dtp_set_option(self._h, name.encode(), int(value)), f"dtp_set_option({name})")
 
+    def profile_dump(self, path: str):
+        self._check(self._lib.dtp_profile_dump(self._h, path.encode()), "dtp_profile_dump")
+
     KINDS = ("other", "contraction", "groupnorm", "layernorm", "softmax", "attn_small")
 
     def profile(self):

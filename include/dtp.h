@@ -155,6 +155,8 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
 /* counters: "launches" (kernels launched by this engine so far), "stamps", "arena_peak", "arena_bytes" */
 long long dtp_get_counter(dtp_handle* h, const char* name);
 int dtp_set_option(dtp_handle* h, const char* name, int value);
+/* after dtp_set_option(h, "profile", 1): CSV of device time per distinct op (label, calls, microseconds), slowest first */
+int dtp_profile_dump(dtp_handle* h, const char* path);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,51 @@
+"""One warm + one profiled stamp of the benchmark workload; writes the per-op device-time table (CUDA events around every
+launch on the launching stream) to gpurun_out/<tag>_ops.csv. Under `ncu --metrics gpu__time_duration.sum` the same
+command yields the launch list committed next to it.
+    python profiles/profile_stamp.py [--resolution 512] [--denoise-steps 20] [--tag r1] [--stamps 1] [--no-op-profile]"""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from diffusiontexturepainting_b200 import weights as W  # noqa: E402
+from diffusiontexturepainting_b200.testdata import make_canvas, smooth_image  # noqa: E402
+from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--resolution", type=int, default=512)
+ap.add_argument("--denoise-steps", type=int, default=20)
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--tag", default="r1")
+ap.add_argument("--stamps", type=int, default=1)
+ap.add_argument("--no-op-profile", action="store_true")
+a = ap.parse_args()
+R, S, B = a.resolution, a.denoise_steps, a.batch
+model = TRTConditionalInpainter(R, device=0, model_config=W.sd15_config(), max_batch_size=B)
+model.pipeline.strict_schedule = True
+model.set_brush(smooth_image(1, 3, R))
+canvas = make_canvas(B, R).cuda()
+lat = torch.randn(B, 4, R // 8, R // 8, generator=torch.Generator().manual_seed(42)).cuda()
+model.pipeline.update_infer_settings(S, 2.0, 1.0, S)
+model.pipeline._push_schedule(1.0)
+out = torch.empty(B, 3, R, R, device="cuda")
+eng = model.engine
+eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+torch.cuda.synchronize()
+if not a.no_op_profile:
+    eng.set_option("profile", 1)
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(a.stamps):
+    eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+t1.record()
+torch.cuda.synchronize()
+print("ms per stamp (with per-op events)" if not a.no_op_profile else "ms per stamp", t0.elapsed_time(t1) / a.stamps)
+if not a.no_op_profile:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    path = os.path.join(ROOT, "gpurun_out", f"{a.tag}_ops.csv")
+    eng.profile_dump(path)
+    print(eng.profile())
+    print(open(path).read()[:6000])
