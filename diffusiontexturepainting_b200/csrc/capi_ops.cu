@@ -11,6 +11,7 @@
 using namespace dtp;
 
 namespace {
+long long* g_dbg = nullptr;
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
 char g_err[512] = "";
@@ -44,6 +45,7 @@ int finish(GemmOp& op, int rc_setup, const float* bias, const void* residual, in
     op.p.hw_out = hw_out;
     if (ensure_ws(gemm_workspace_bytes(&op))) return -1;
     op.p.workspace = g_ws;
+    op.p.dbg = g_dbg;
     int r = gemm_launch(&op, st);
     if (r) snprintf(g_err, sizeof(g_err), "gemm launch: %s", gemm_last_error());
     return r;
@@ -53,6 +55,11 @@ int finish(GemmOp& op, int rc_setup, const float* bias, const void* residual, in
 extern "C" {
 
 const char* dtp_ops_last_error(void) { return g_err; }
+
+// tuning aid: when set, every contraction launched through the operator entry points records per-CTA globaltimer
+// checkpoints into dbg[cta*8 + slot] (slot 0 start, 1 setup done, 2 first operands landed, 3 MMAs issued,
+// 4 accumulator ready, 5 epilogue done, 6 TMEM released)
+void dtp_ops_set_debug_buffer(long long* dbg) { g_dbg = dbg; }
 
 int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, int K1, int M, const void* Wt, int ldw,
                   int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,

@@ -114,6 +114,18 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     }
 }
 
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_MARK(slot)                                                                                         \
+    do {                                                                                                       \
+        if (p.dbg != nullptr)                                                                                  \
+            p.dbg[(static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x +      \
+                   blockIdx.x) * 8 + (slot)] = gtime();                                                        \
+    } while (0)
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -151,6 +163,7 @@ __global__ void __launch_bounds__(192, 1)
         img0 = tn * p.bn;
     }
 
+    if (threadIdx.x == 0) DBG_MARK(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
@@ -167,6 +180,7 @@ __global__ void __launch_bounds__(192, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) DBG_MARK(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -217,6 +231,7 @@ __global__ void __launch_bounds__(192, 1)
             uint32_t phase = 0;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
                 mbar_wait_bounded(&full_bar[stage], phase);
+                if (kb == kb_begin) DBG_MARK(2);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const uint32_t sb = sa + A_BYTES;
@@ -236,6 +251,7 @@ __global__ void __launch_bounds__(192, 1)
                 }
             }
             umma_commit(tmem_full_bar);
+            DBG_MARK(3);
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
@@ -257,6 +273,7 @@ __global__ void __launch_bounds__(192, 1)
         const long long out_off = static_cast<long long>(z1) * p.out_zs1 + static_cast<long long>(z2) * p.out_zs2;
         mbar_wait_bounded(tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) DBG_MARK(4);
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             if (n0 + c >= p.N) break;
@@ -285,9 +302,11 @@ __global__ void __launch_bounds__(192, 1)
             }
         }
     }
+    if (threadIdx.x == 64) DBG_MARK(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
+    if (threadIdx.x == 32) DBG_MARK(6);
 }
 
 // sums split-K partials and runs the epilogue; one thread per (row, 32-column chunk)

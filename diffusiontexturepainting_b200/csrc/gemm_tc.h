@@ -57,6 +57,7 @@ struct GemmParams {
     const __half* residual;   // [M, ldr] fp16, nullable
     void* out;                // fp16 [M, ldc] (default) / fp32 variants
     float* workspace;         // [batch*splits, Mpad, N] fp32
+    long long* dbg;           // optional: per-CTA globaltimer checkpoints [ctas][8] (tuning aid), nullable
 };
 
 struct GemmOp {
