@@ -16,54 +16,119 @@ static char g_gemm_err[256] = "";
 const char* gemm_last_error() { return g_gemm_err; }
 
 // ------------------------------------------------------------------------------------------------------------
-// epilogue (shared by the main kernel and the split-K finalize kernel)
+// epilogue: one thread owns one output row and 32 consecutive columns of it (the tcgen05.ld 32x32b shape).
+// Shared by the main kernel and the split-K finalize kernel. No runtime-indexed register arrays: everything below
+// unrolls to compile-time register indices (the first version kept v[] in local memory and spent ~6 us per chunk).
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float quick_gelu_fast(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+
+__device__ __forceinline__ void store_half_chunk(__half* out, const float (&v)[32], int ncols, bool vec_ok) {
+    if (ncols == 32 && vec_ok) {
+        uint4* o = reinterpret_cast<uint4*>(out);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half2 a = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
+            __half2 b = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+            __half2 c = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
+            __half2 d = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&a);
+            u.y = *reinterpret_cast<uint32_t*>(&b);
+            u.z = *reinterpret_cast<uint32_t*>(&c);
+            u.w = *reinterpret_cast<uint32_t*>(&d);
+            o[i] = u;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols) out[i] = __float2half_rn(v[i]);
+    }
+}
+
+// bias_chunk: 32 floats for columns col0.. (shared memory in the main kernel, global in the finalize kernel), or nullptr
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long out_off, int row, int col0,
-                                                 float (&v)[32]) {
+                                                 float (&v)[32], const float* bias_chunk) {
     const int N = p.N;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
     const int flags = p.flags;
-    const float rowbias = (p.bias != nullptr && (flags & EPI_BIAS_M)) ? __ldg(p.bias + row) : 0.0f;
+    const float alpha = p.alpha;
+    // residual loads first: their latency overlaps the arithmetic below
+    const bool has_res = p.residual != nullptr;
+    uint4 rraw[4];
+    const __half* rp = has_res ? p.residual + static_cast<long long>(row) * p.ldr + col0 : nullptr;
+    const bool res_vec = has_res && ncols == 32 && (p.ldr & 7) == 0;
+    if (res_vec) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        float x = v[i] * p.alpha;
-        if (p.bias != nullptr) {
-            if (flags & EPI_BIAS_M)
-                x += rowbias;
-            else if (i < ncols)
-                x += __ldg(p.bias + col0 + i);
-        }
-        if (flags & EPI_GELU) x = gelu_erf_f(x);
-        if (flags & EPI_QUICKGELU) x = quick_gelu_f(x);
-        if (flags & EPI_SILU) x = silu_f(x);
-        v[i] = x;
+        for (int i = 0; i < 4; ++i) rraw[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+    }
+    if (flags & EPI_BIAS_M) {
+        const float rb = p.bias ? __ldg(p.bias + row) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, rb);
+    } else if (bias_chunk != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, bias_chunk[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= alpha;
     }
     if (flags & EPI_GEGLU) {
         // columns [0,16) hold a_j, [16,32) hold the gates g_j of the same 16 outputs
-        const int oc0 = col0 >> 1;
-        __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + oc0;
-        __align__(16) __half h[16];
+        __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + (col0 >> 1);
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = __float2half_rn(v[i] * gelu_erf_f(v[16 + i]));
+        for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
         if ((p.ldc & 7) == 0) {
-            reinterpret_cast<uint4*>(out)[0] = reinterpret_cast<const uint4*>(h)[0];
-            reinterpret_cast<uint4*>(out)[1] = reinterpret_cast<const uint4*>(h)[1];
+            uint4* d = reinterpret_cast<uint4*>(out);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                __half2 a = __floats2half2_rn(o[8 * i + 0], o[8 * i + 1]);
+                __half2 b = __floats2half2_rn(o[8 * i + 2], o[8 * i + 3]);
+                __half2 c = __floats2half2_rn(o[8 * i + 4], o[8 * i + 5]);
+                __half2 e = __floats2half2_rn(o[8 * i + 6], o[8 * i + 7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&a);
+                u.y = *reinterpret_cast<uint32_t*>(&b);
+                u.z = *reinterpret_cast<uint32_t*>(&c);
+                u.w = *reinterpret_cast<uint32_t*>(&e);
+                d[i] = u;
+            }
         } else {
-            for (int i = 0; i < 16; ++i) out[i] = h[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) out[i] = __float2half_rn(o[i]);
         }
         return;
     }
-    if (p.residual != nullptr) {
-        const __half* r = p.residual + static_cast<long long>(row) * p.ldr + col0;
-        if (ncols == 32 && (p.ldr & 7) == 0) {
-            __align__(16) __half h[32];
+    if (flags & (EPI_GELU | EPI_QUICKGELU | EPI_SILU)) {
+        if (flags & EPI_GELU) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(h)[i] = __ldg(reinterpret_cast<const uint4*>(r) + i);
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
+        } else if (flags & EPI_QUICKGELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __half2float(h[i]);
+            for (int i = 0; i < 32; ++i) v[i] = quick_gelu_fast(v[i]);
         } else {
-            for (int i = 0; i < ncols; ++i) v[i] += __half2float(r[i]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
+        }
+    }
+    if (has_res) {
+        if (res_vec) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2* h2 = reinterpret_cast<const __half2*>(&rraw[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    v[8 * i + 2 * j] += f.x;
+                    v[8 * i + 2 * j + 1] += f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols) v[i] += __half2float(rp[i]);
         }
     }
     if (flags & EPI_IMG01) {
@@ -73,32 +138,27 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     if (flags & EPI_OUT_F32_NCHW) {
         float* out = reinterpret_cast<float*>(p.out) + out_off;
         const int img = row / p.hw_out, pix = row - img * p.hw_out;
+        float* o = out + (static_cast<long long>(img) * N + col0) * p.hw_out + pix;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < ncols) out[(static_cast<long long>(img) * N + col0 + i) * p.hw_out + pix] = v[i];
+            if (i < ncols) o[static_cast<long long>(i) * p.hw_out] = v[i];
         return;
     }
     if (flags & EPI_OUT_F32) {
         float* out = reinterpret_cast<float*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
-        if (ncols == 32 && (p.ldc & 3) == 0) {
+        if (ncols == 32 && (p.ldc & 3) == 0 && (out_off & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
                 reinterpret_cast<float4*>(out)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
-            for (int i = 0; i < ncols; ++i) out[i] = v[i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols) out[i] = v[i];
         }
         return;
     }
     __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
-    if (ncols == 32 && (p.ldc & 7) == 0 && ((out_off & 7) == 0)) {
-        __align__(16) __half h[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(v[i]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(h)[i];
-    } else {
-        for (int i = 0; i < ncols; ++i) out[i] = __float2half_rn(v[i]);
-    }
+    store_half_chunk(out, v, ncols, (p.ldc & 7) == 0 && (out_off & 7) == 0);
 }
 
 // bounded mbarrier wait: a descriptor / byte-count bug must trap, not hang the GPU
@@ -106,11 +166,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("dtp gemm: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   threadIdx.x);
-            __trap();
-        }
+        if (clock64() - t0 > 8000000000LL) __trap();
     }
 }
 
@@ -119,49 +175,67 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define DBG_MARK(slot)                                                                                         \
-    do {                                                                                                       \
-        if (p.dbg != nullptr)                                                                                  \
-            p.dbg[(static_cast<long long>(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x +      \
-                   blockIdx.x) * 8 + (slot)] = gtime();                                                        \
+#define DBG_MARK(slot)                                                                     \
+    do {                                                                                   \
+        if (p.dbg != nullptr) p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = gtime(); \
     } while (0)
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct TileCoord {
+    int m_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
+};
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+    TileCoord c;
+    c.m_tile = t % p.grid_m;
+    int r = t / p.grid_m;
+    const int n_tile = r % p.grid_n;
+    r /= p.grid_n;
+    c.zsplit = r % p.splits;
+    c.zb = r / p.splits;
+    c.z1 = c.zb % p.nz1;
+    c.z2 = c.zb / p.nz1;
+    c.n0 = n_tile * BN;
+    c.kb_begin = static_cast<int>(static_cast<long long>(c.zsplit) * p.num_kb / p.splits);
+    c.kb_end = static_cast<int>(static_cast<long long>(c.zsplit + 1) * p.num_kb / p.splits);
+    c.x0 = c.y0 = c.img0 = 0;
+    if (p.mode == 1) {
+        const int tx = c.m_tile % p.tiles_x;
+        const int ty = (c.m_tile / p.tiles_x) % p.tiles_y;
+        const int tn = c.m_tile / (p.tiles_x * p.tiles_y);
+        c.x0 = tx * p.bw;
+        c.y0 = ty * p.bh;
+        c.img0 = tn * p.bn;
+    }
+    return c;
+}
+
+// Persistent kernel: grid = min(tiles, SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
+// Two TMEM accumulators (BN columns each) let the epilogue of tile i overlap the mainloop of tile i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                   const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TM_COLS = BN < 32 ? 32 : BN;
+    constexpr int TM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    constexpr int B_CHUNKS = (BN + 63) / 64;  // MN-major B: 64-column boxes
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int zsplit = blockIdx.z % p.splits;
-    const int zb = blockIdx.z / p.splits;
-    const int z1 = zb % p.nz1, z2 = zb / p.nz1;
-    const int kb_begin = static_cast<int>(static_cast<long long>(zsplit) * p.num_kb / p.splits);
-    const int kb_end = static_cast<int>(static_cast<long long>(zsplit + 1) * p.num_kb / p.splits);
-    const int m_tile = blockIdx.x;
-    const int n0 = blockIdx.y * BN;
     const bool b_mn = (p.flags & GEMM_B_MN) != 0;
-
-    int x0 = 0, y0 = 0, img0 = 0;
-    if (p.mode == 1) {
-        const int tx = m_tile % p.tiles_x;
-        const int ty = (m_tile / p.tiles_x) % p.tiles_y;
-        const int tn = m_tile / (p.tiles_x * p.tiles_y);
-        x0 = tx * p.bw;
-        y0 = ty * p.bh;
-        img0 = tn * p.bn;
-    }
+    const int total_tiles = p.total_tiles;
 
     if (threadIdx.x == 0) DBG_MARK(0);
     if (warp == 0 && lane == 0) {
@@ -172,7 +246,10 @@ __global__ void __launch_bounds__(192, 1)
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
@@ -186,40 +263,44 @@ __global__ void __launch_bounds__(192, 1)
         if (lane == 0) {
             // ------------------------------ TMA producer ------------------------------
             const uint32_t a_bytes = (p.mode == 1) ? static_cast<uint32_t>(p.rows_valid) * 128u : A_BYTES;
+            const uint32_t b_bytes = b_mn ? static_cast<uint32_t>(B_CHUNKS) * 8192u : B_BYTES;
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], a_bytes + B_BYTES);
-                if (p.mode == 1) {
-                    const int tap = kb / p.cblocks;
-                    const int cb = kb - tap * p.cblocks;
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    if (cb < p.cblocks0)
-                        tma_load_4d(sa, &mapA0, &full_bar[stage], cb * 64, x0 + kx - 1, y0 + ky - 1, img0);
-                    else
-                        tma_load_4d(sa, &mapA1, &full_bar[stage], (cb - p.cblocks0) * 64, x0 + kx - 1, y0 + ky - 1,
-                                    img0);
-                } else {
-                    const int za = p.a_batched ? z1 : 0, zb2 = p.a_batched ? z2 : 0;
-                    if (kb < p.cblocks0)
-                        tma_load_4d(sa, &mapA0, &full_bar[stage], kb * 64, m_tile * 128, za, zb2);
-                    else
-                        tma_load_4d(sa, &mapA1, &full_bar[stage], (kb - p.cblocks0) * 64, m_tile * 128, za, zb2);
-                }
-                const int bz1 = p.b_batched ? z1 : 0, bz2 = p.b_batched ? z2 : 0;
-                if (!b_mn) {
-                    tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, n0, bz1, bz2);
-                } else {
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile<BN>(p, t);
+                const int za = p.a_batched ? c.z1 : 0, za2 = p.a_batched ? c.z2 : 0;
+                const int bz1 = p.b_batched ? c.z1 : 0, bz2 = p.b_batched ? c.z2 : 0;
+                for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
+                    mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                    if (p.mode == 1) {
+                        const int tap = kb / p.cblocks;
+                        const int cb = kb - tap * p.cblocks;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        if (cb < p.cblocks0)
+                            tma_load_4d(sa, &mapA0, &full_bar[stage], cb * 64, c.x0 + kx - 1, c.y0 + ky - 1, c.img0);
+                        else
+                            tma_load_4d(sa, &mapA1, &full_bar[stage], (cb - p.cblocks0) * 64, c.x0 + kx - 1,
+                                        c.y0 + ky - 1, c.img0);
+                    } else {
+                        if (kb < p.cblocks0)
+                            tma_load_4d(sa, &mapA0, &full_bar[stage], kb * 64, c.m_tile * 128, za, za2);
+                        else
+                            tma_load_4d(sa, &mapA1, &full_bar[stage], (kb - p.cblocks0) * 64, c.m_tile * 128, za, za2);
+                    }
+                    if (!b_mn) {
+                        tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j)
-                        tma_load_4d(sb + j * 8192, &mapB, &full_bar[stage], n0 + j * 64, kb * 64, bz1, bz2);
-                }
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                        for (int j = 0; j < B_CHUNKS; ++j)
+                            tma_load_4d(sb + j * 8192, &mapB, &full_bar[stage], c.n0 + j * 64, kb * 64, bz1, bz2);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -229,80 +310,123 @@ __global__ void __launch_bounds__(192, 1)
             const uint32_t idesc = umma_idesc_f16(128, BN, 0, b_mn ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait_bounded(&full_bar[stage], phase);
-                if (kb == kb_begin) DBG_MARK(2);
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            bool first = true;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile<BN>(p, t);
+                mbar_wait_bounded(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const uint32_t sb = sa + A_BYTES;
-                const uint64_t adesc = umma_desc_k_sw128(sa);
-                const uint64_t bdesc = b_mn ? umma_desc_mn_sw128(sb, 8192) : umma_desc_k_sw128(sb);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
+                    mbar_wait_bounded(&full_bar[stage], phase);
+                    if (first) {
+                        DBG_MARK(2);
+                        first = false;
+                    }
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t sb = sa + A_BYTES;
+                    const uint64_t adesc = umma_desc_k_sw128(sa);
+                    const uint64_t bdesc = b_mn ? umma_desc_mn_sw128(sb, 8192) : umma_desc_k_sw128(sb);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // advance 16 K-elements: 32 B inside the swizzle atom (K-major) / two 8-row groups (MN-major)
-                    const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
-                    const uint64_t bd = bdesc + static_cast<uint64_t>(b_mn ? k * 128 : k * 2);
-                    umma_f16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 16 K-elements: 32 B inside the swizzle atom (K-major) / two 8-row groups (MN-major)
+                        const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
+                        const uint64_t bd = bdesc + static_cast<uint64_t>(b_mn ? k * 128 : k * 2);
+                        umma_f16(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+                umma_commit(&tmem_full_bar[acc]);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
                 }
             }
-            umma_commit(tmem_full_bar);
             DBG_MARK(3);
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        int row = -1;
-        if (p.mode == 1) {
-            if (r < p.rows_valid) {
-                const int w = r % p.bw;
-                const int hh = (r / p.bw) % p.bh;
-                const int nn = r / (p.bw * p.bh);
-                const int img = img0 + nn;
-                if (img < p.Nimg) row = (img * p.H + y0 + hh) * p.W + x0 + w;
+        const int et = threadIdx.x - 64;  // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0 && p.splits == 1;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord c = decode_tile<BN>(p, t);
+            int row = -1;
+            if (p.mode == 1) {
+                if (r < p.rows_valid) {
+                    const int w = r % p.bw;
+                    const int hh = (r / p.bw) % p.bh;
+                    const int nn = r / (p.bw * p.bh);
+                    const int img = c.img0 + nn;
+                    if (img < p.Nimg) row = (img * p.H + c.y0 + hh) * p.W + c.x0 + w;
+                }
+            } else {
+                const int m = c.m_tile * 128 + r;
+                if (m < p.M) row = m;
             }
-        } else {
-            const int m = m_tile * 128 + r;
-            if (m < p.M) row = m;
-        }
-        const long long out_off = static_cast<long long>(z1) * p.out_zs1 + static_cast<long long>(z2) * p.out_zs2;
-        mbar_wait_bounded(tmem_full_bar, 0);
-        tc_fence_after();
-        if (threadIdx.x == 64) DBG_MARK(4);
+            const long long out_off = static_cast<long long>(c.z1) * p.out_zs1 + static_cast<long long>(c.z2) * p.out_zs2;
+            if (col_bias) {
+                epi_bar_sync();  // previous tile's readers are done with sbias
+                for (int i = et; i < BN; i += 128) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
+                epi_bar_sync();
+            }
+            mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            if (t == static_cast<int>(blockIdx.x) && et == 0) DBG_MARK(4);
+            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            if (n0 + c >= p.N) break;
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), raw);
-            tmem_ld_wait();
-            if (row >= 0) {
-                float v[32];
+            for (int cc = 0; cc < BN; cc += 32) {
+                if (c.n0 + cc >= p.N) break;
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc), raw);
+                tmem_ld_wait();
+                if (cc + 32 >= BN || c.n0 + cc + 32 >= p.N) {
+                    // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (row >= 0) {
+                    float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                if (p.splits > 1) {
-                    float* ws = p.workspace +
-                                (static_cast<long long>(blockIdx.z) * p.M + row) * static_cast<long long>(p.N) + n0 + c;
-                    const int ncols = min(32, p.N - (n0 + c));
-                    if (ncols == 32 && (p.N & 3) == 0) {
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (p.splits > 1) {
+                        float* ws = p.workspace +
+                                    (static_cast<long long>(c.zb * p.splits + c.zsplit) * p.M + row) *
+                                        static_cast<long long>(p.N) +
+                                    c.n0 + cc;
+                        const int ncols = min(32, p.N - (c.n0 + cc));
+                        if (ncols == 32 && (p.N & 3) == 0) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            reinterpret_cast<float4*>(ws)[i] =
-                                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(ws)[i] =
+                                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < ncols) ws[i] = v[i];
+                        }
                     } else {
-                        for (int i = 0; i < ncols; ++i) ws[i] = v[i];
+                        epilogue_store32(p, out_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
                     }
-                } else {
-                    epilogue_store32(p, out_off, row, n0 + c, v);
                 }
             }
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
         }
+        if (et == 0) DBG_MARK(5);
     }
-    if (threadIdx.x == 64) DBG_MARK(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
@@ -310,7 +434,7 @@ __global__ void __launch_bounds__(192, 1)
 }
 
 // sums split-K partials and runs the epilogue; one thread per (row, 32-column chunk)
-__global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const __grid_constant__ GemmParams p) {
     const int chunks = (p.N + 31) / 32;
     const long long total = static_cast<long long>(p.nz1) * p.nz2 * p.M * chunks;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -337,12 +461,20 @@ __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const GemmPar
                 v[4 * i + 3] += t.w;
             }
         } else {
-            for (int i = 0; i < ncols; ++i) v[i] += ws[i];
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < ncols) v[i] += ws[i];
         }
+    }
+    float b[32];
+    const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
+    if (col_bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(p.bias + col0 + i) : 0.0f;
     }
     const int z1 = zb % p.nz1, z2 = zb / p.nz1;
     const long long out_off = static_cast<long long>(z1) * p.out_zs1 + static_cast<long long>(z2) * p.out_zs2;
-    epilogue_store32(p, out_off, row, col0, v);
+    epilogue_store32(p, out_off, row, col0, v, col_bias ? b : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -407,7 +539,9 @@ static void params_defaults(GemmParams& p) {
     p.alpha = 1.0f;
 }
 
-static int fix_bn(int BN) { return (BN == 32 || BN == 64 || BN == 128 || BN == 256) ? BN : 128; }
+static int fix_bn(int BN) {
+    return (BN == 32 || BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256) ? BN : 128;
+}
 
 // 2-D (K inner, rows outer) map expressed as 4-D with unit batch dims
 static int map_rows(CUtensorMap* m, const __half* base, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows) {
@@ -511,6 +645,7 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
     GemmParams& p = op->p;
     BN = fix_bn(BN);
     if (b_mn && BN < 64) BN = 64;
+    if (b_mn && BN == 160) BN = 192;  // MN-major B is loaded in 64-column boxes
     p.M = M;
     p.N = N;
     p.num_kb = (K + 63) / 64;
@@ -555,32 +690,62 @@ size_t gemm_workspace_bytes(const GemmOp* op) {
 }
 
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
+    // Cost model (cycles) of the persistent kernel: per k-block the tensor pipe needs 2*BN cycles (128 x BN x 64 MACs at
+    // 4096 MAC/clk) and the TMA feed (16 KB of A + 128*BN B of B) about 64 B/clk per SM (measured); the epilogue of a
+    // tile (~350 clk per 32-column chunk) overlaps the next tile's mainloop.
     const int kSMs = 148;
-    int bn = 32;
-    if (N > 32) bn = 64;
-    if (N > 64) bn = 128;
-    if (N > 128) {
-        // prefer the 256-wide tile (half the A re-reads per flop) once it still fills the machine
-        const int t256 = mtiles * ((N + 255) / 256);
-        bn = (t256 >= kSMs) ? 256 : 128;
-        if (bn == 128 && mtiles * ((N + 127) / 128) < kSMs / 2 && (flags & GEMM_B_MN) == 0) bn = 64;
+    static const int cand_k[] = {32, 64, 128, 160, 192, 256};
+    static const int cand_mn[] = {64, 128, 192, 256};
+    const bool mn = (flags & GEMM_B_MN) != 0;
+    const int* cand = mn ? cand_mn : cand_k;
+    const int ncand = mn ? 4 : 6;
+    long long best_cost = -1;
+    int best = cand[ncand - 1];
+    for (int i = 0; i < ncand; ++i) {
+        const int bn = cand[i];
+        if (bn >= 64 && bn - 32 >= ((N + 31) / 32) * 32) continue;  // mostly padding
+        const long long gn = (N + bn - 1) / bn;
+        const long long tiles = static_cast<long long>(mtiles) * gn;
+        const long long t_mma = 2LL * bn;
+        const long long t_tma = (16384 + 128LL * bn) / 64;
+        const long long t_main = num_kb * (t_mma > t_tma ? t_mma : t_tma);
+        const long long t_epi = 300 + (bn / 32) * 350LL;
+        const long long t_tile = (t_main > t_epi ? t_main : t_epi) + 200;
+        const long long per_cta = (tiles + kSMs - 1) / kSMs;
+        const long long cost = per_cta * t_tile + t_epi;
+        if (best_cost < 0 || cost <= best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
     }
-    const int tiles = mtiles * ((N + bn - 1) / bn);
+    const long long tiles = static_cast<long long>(mtiles) * ((N + best - 1) / best);
     int sp = 1;
-    if (tiles < kSMs && num_kb >= 8) {
-        sp = kSMs / tiles;
+    if (tiles * 2 <= kSMs && num_kb >= 8) {
+        sp = static_cast<int>(kSMs / tiles);
         if (sp > num_kb / 4) sp = num_kb / 4;
         if (sp > 16) sp = 16;
         if (sp < 1) sp = 1;
     }
-    *BN = bn;
+    *BN = best;
     *splits = sp;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 template <int BN, int STAGES>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
-    constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+    constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
@@ -591,8 +756,16 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    const GemmParams& p = op->p;
-    dim3 grid(op->grid_m, (p.N + BN - 1) / BN, p.nz1 * p.nz2 * p.splits);
+    GemmParams p = op->p;
+    p.grid_m = op->grid_m;
+    p.grid_n = (p.N + BN - 1) / BN;
+    const long long tiles = static_cast<long long>(p.grid_m) * p.grid_n * p.nz1 * p.nz2 * p.splits;
+    if (tiles > 0x7fffffffLL) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "too many tiles");
+        return -24;
+    }
+    p.total_tiles = static_cast<int>(tiles);
+    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
     gemm_tc_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(op->mapA0, op->mapA1, op->mapB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -613,6 +786,8 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
         case 32: r = launch_cfg<32, 8>(op, stream); break;
         case 64: r = launch_cfg<64, 8>(op, stream); break;
         case 128: r = launch_cfg<128, 6>(op, stream); break;
+        case 160: r = launch_cfg<160, 5>(op, stream); break;
+        case 192: r = launch_cfg<192, 5>(op, stream); break;
         default: r = launch_cfg<256, 4>(op, stream); break;
     }
     if (r) return r;

@@ -58,12 +58,13 @@ struct GemmParams {
     void* out;                // fp16 [M, ldc] (default) / fp32 variants
     float* workspace;         // [batch*splits, Mpad, N] fp32
     long long* dbg;           // optional: per-CTA globaltimer checkpoints [ctas][8] (tuning aid), nullable
+    int grid_m, grid_n, total_tiles;  // filled at launch: tile grid of the persistent scheduler
 };
 
 struct GemmOp {
     CUtensorMap mapA0, mapA1, mapB;
     GemmParams p;
-    int BN;      // 32, 64, 128 or 256
+    int BN;      // 32, 64, 128, 160, 192 or 256
     int grid_m;  // number of 128-row tiles
 };
 

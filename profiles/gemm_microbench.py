@@ -22,7 +22,7 @@ def run_linear(M, N, K, BN, splits=1, flags=0, reps=20, stages=False):
     W = torch.randn(N, K, device=dev).half()
     out = torch.empty(M, N // 2 if flags & 8 else N, device=dev, dtype=torch.float16)
     bias = torch.randn(N, device=dev)
-    nct = ((M + 127) // 128) * ((N + BN - 1) // BN) * splits
+    nct = ((M + 127) // 128) * ((N + max(BN, 32) - 1) // max(BN, 32)) * splits
     dbg = torch.zeros(nct, 8, dtype=torch.int64, device=dev)
 
     def call():
@@ -61,9 +61,10 @@ def run_linear(M, N, K, BN, splits=1, flags=0, reps=20, stages=False):
 
 if __name__ == "__main__":
     st = "--stages" in sys.argv
-    for (M, N, K, BN) in [(12288, 320, 320, 256), (12288, 320, 320, 64), (12288, 320, 1280, 256), (768, 1280, 1280, 64),
+    for (M, N, K, BN) in [(12288, 320, 320, 256), (12288, 320, 320, 160), (12288, 320, 320, 64), (12288, 320, 1280, 160),
+                          (12288, 320, 2880, 160), (12288, 320, 2880, 128), (768, 1280, 1280, 64), (768, 1280, 11520, 128),
                           (12288, 2560, 320, 256), (4096, 4096, 64, 256), (8192, 8192, 8192, 256),
-                          (8192, 8192, 8192, 128)]:
+                          (8192, 8192, 8192, 192), (8192, 8192, 8192, 128)]:
         run_linear(M, N, K, BN, stages=st)
     run_linear(12288, 2560, 320, 256, flags=8, stages=st)
     run_linear(192, 1280, 11520, 64, splits=7, stages=st)

@@ -47,7 +47,7 @@ def linear_op(A, W, bias=None, residual=None, flags=0, alpha=1.0, BN=0, splits=1
     return out
 
 
-@pytest.mark.parametrize("BN", [0, 32, 64, 128, 256])
+@pytest.mark.parametrize("BN", [0, 32, 64, 128, 160, 192, 256])
 @pytest.mark.parametrize("M,N,K", [(300, 200, 320), (128, 256, 64), (1000, 520, 1280), (7, 40, 72)])
 def test_linear_plain(M, N, K, BN):
     A, W, b = h(rnd(M, K)), h(rnd(N, K, scale=K ** -0.5)), rnd(N)
@@ -141,7 +141,7 @@ def test_conv3x3(n, H, W, cin, cout):
     assert rel_l2(out, conv_ref(x, w, cin, b)) < 2e-3
 
 
-@pytest.mark.parametrize("splits,BN", [(1, 128), (4, 128), (3, 64), (2, 256)])
+@pytest.mark.parametrize("splits,BN", [(1, 128), (4, 128), (3, 64), (2, 256), (1, 160), (2, 192)])
 def test_conv3x3_dual_source_residual_splitk(splits, BN):
     n, H, W, c0, c1, cout = 3, 8, 8, 128, 64, 256
     x0, x1 = h(rnd(n, H, W, c0)), h(rnd(n, H, W, c1, seed=5))
