@@ -21,6 +21,7 @@ _OPS = {
     "dtp_op_layernorm": [vp, i32, i32, vp, vp, f32, vp, vp],
     "dtp_op_softmax": [vp, i64, i32, i32, vp],
     "dtp_op_attn_small": [vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, i64, i64, i64, vp, f32, vp],
+    "dtp_op_flash_attn": [vp, vp, vp, i32, i64, vp, i32, i64, i32, i32, i32, i32, vp],
     "dtp_op_upsample2x": [vp, i32, i32, i32, i32, vp, vp],
     "dtp_op_im2col_s2": [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp],
     "dtp_op_ddim_step": [vp, vp, vp, i32, i32, f32, f32, f32, f32, vp],
@@ -80,7 +81,7 @@ def lib():
 
 
 def exported_symbols():
-    return list(_OPS) + list(_PIPE) + ["dtp_ops_last_error", "dtp_last_error"]
+    return list(_OPS) + list(_PIPE) + ["dtp_ops_last_error", "dtp_last_error", "dtp_ops_set_debug_buffer"]
 
 
 def ptr(t):

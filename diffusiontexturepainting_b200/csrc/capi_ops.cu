@@ -127,6 +127,21 @@ int dtp_op_attn_small(const void* q, int ldq, const void* k, int ldk, const void
                              nkv, heads, d, batch, q_bs, kv_bs, o_bs, kv_index, scale, (cudaStream_t)stream);
 }
 
+int dtp_op_flash_attn(const void* q, const void* k, const void* v, int ld, long long bs, void* out, int ldo,
+                      long long o_bs, int seq, int heads, int d, int batch, void* stream) {
+    FlashOp op;
+    if (flash_attn_setup(&op, (const __half*)q, (const __half*)k, (const __half*)v, ld, bs, (__half*)out, ldo, o_bs, seq,
+                         heads, d, batch)) {
+        snprintf(g_err, sizeof(g_err), "%s", flash_last_error());
+        return -1;
+    }
+    if (flash_attn_launch(&op, (cudaStream_t)stream)) {
+        snprintf(g_err, sizeof(g_err), "%s", flash_last_error());
+        return -1;
+    }
+    return 0;
+}
+
 int dtp_op_upsample2x(const void* x, int Nimg, int H, int W, int C, void* out, void* stream) {
     return launch_upsample2x((const __half*)x, Nimg, H, W, C, (__half*)out, (cudaStream_t)stream);
 }

@@ -1,0 +1,344 @@
+// Flash self-attention for the UNet transformer blocks on tcgen05 (sm_100a): softmax(Q K^T / sqrt(d)) V with the score
+// tile living only in TMEM / registers (never in HBM). Replaces TensorRT's fused MHA for attn1 of the 16
+// BasicTransformerBlocks (trt_inference/models.py:1158 keeps the native fMHA path; graph: SURVEY.md Appendix A.1).
+//
+// One CTA = one (sample, head, 128-query tile). Warp 0 (one lane) feeds Q once and the K / V tiles of each 128-key block
+// by TMA; warp 1 allocates TMEM and (one lane) issues  S = Q K^T  (fp32 in TMEM columns [0,128)) and  O += P V  (columns
+// [128, 128+dN)); warps 2..5 (one thread per query row) run the online softmax: two passes over S with tcgen05.ld, P
+// written as fp16 into a 128-byte-swizzled shared tile that is the A operand of the second MMA, lazy rescaling of O
+// (only when the running maximum grows by more than 2^8, exact because the same stale maximum scales P and the row sum).
+// Head dims 40 / 80 / 160 are zero-padded to 64 / 128 / 192 by TMA out-of-bounds fill; only ceil(d/16) k-steps are issued.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "gemm_tc.h"
+#include "kernels.h"
+
+namespace dtp {
+
+struct FlashParams {
+    int seq_q, seq_kv, heads, batch, d;
+    int dN;           // accumulator columns of O: d rounded up to 16
+    int ksteps_qk;    // ceil(d / 16)
+    float scale_log2;  // softmax scale * log2(e)
+    __half* out;
+    int ldo;
+    long long o_bs;
+};
+
+__device__ __forceinline__ void fa_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// DCH: 64-wide chunks of the (padded) head dim; KV_STAGES: ring depth of the K and V tiles
+template <int DCH, int KV_STAGES>
+__global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
+    flash_attn_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FlashParams p) {
+    constexpr int TILE_BYTES = DCH * 16384;  // one [128 rows x DCH*64] fp16 operand tile
+    constexpr int P_BYTES = 2 * 16384;       // [128 q x 128 kv] fp16
+    constexpr int TM_COLS = (128 + DCH * 64 <= 256) ? 256 : 512;
+    constexpr uint32_t O_COL = 128;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
+    uint8_t* sP = sV + KV_STAGES * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KV_STAGES;
+    uint64_t* v_full = k_empty + KV_STAGES;
+    uint64_t* v_empty = v_full + KV_STAGES;
+    uint64_t* s_full = v_empty + KV_STAGES;
+    uint64_t* s_empty = s_full + 1;
+    uint64_t* p_full = s_empty + 1;
+    uint64_t* o_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.seq_kv + 127) / 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapQ);
+        tma_prefetch_desc(&mapK);
+        tma_prefetch_desc(&mapV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KV_STAGES; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------ TMA producer ------------------------------
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+            for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * 16384, &mapQ, q_full, c * 64, q0, head, b);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk; ++j) {
+                fa_wait(&k_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sK + st * TILE_BYTES + c * 16384, &mapK, &k_full[st], c * 64, j * 128, head, b);
+                fa_wait(&v_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sV + st * TILE_BYTES + c * 16384, &mapV, &v_full[st], c * 64, j * 128, head, b);
+                if (++st == KV_STAGES) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------ MMA issuer ------------------------------
+            const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+            const uint32_t idesc_o = umma_idesc_f16(128, p.dN, 0, 1);
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            fa_wait(q_full, 0);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk; ++j) {
+                // S = Q K_j^T
+                fa_wait(&k_full[st], ph);
+                fa_wait(s_empty, (j & 1) ^ 1);  // softmax has consumed the previous S
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + st * TILE_BYTES);
+                for (int kk = 0; kk < p.ksteps_qk; ++kk) {
+                    const uint32_t off = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_s,
+                             kk > 0 ? 1u : 0u);
+                }
+                umma_commit(&k_empty[st]);
+                umma_commit(s_full);
+                // O += P_j V_j
+                fa_wait(&v_full[st], ph);
+                fa_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sV + st * TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t poff = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base + O_COL, umma_desc_k_sw128(p_addr + poff),
+                             umma_desc_mn_sw128(v_addr + static_cast<uint32_t>(kk) * 2048u, 16384), idesc_o,
+                             (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&v_empty[st]);
+                umma_commit(o_done);
+                if (++st == KV_STAGES) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------ softmax / correction / epilogue: one thread per query row ------------------------------
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
+        float m_used = -INFINITY, l = 0.0f;
+        uint8_t* prow = sP + r * 128;
+        const int sw = r & 7;
+        for (int j = 0; j < nblk; ++j) {
+            fa_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv_valid = min(128, p.seq_kv - j * 128);
+            // pass 1: block maximum of the scaled scores
+            float bm = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + t_lane + c, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c + i < kv_valid) bm = fmaxf(bm, __uint_as_float(raw[i]) * p.scale_log2);
+            }
+            // P (smem) and O (TMEM) are free once the previous block's second MMA has retired
+            if (j > 0) fa_wait(o_done, (j - 1) & 1);
+            tc_fence_after();
+            bool need = false;
+            float factor = 1.0f;
+            if (j == 0) {
+                m_used = bm;
+            } else if (bm > m_used + 8.0f) {
+                need = true;
+                factor = exp2f(m_used - bm);
+                m_used = bm;
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                l *= factor;
+                for (int c = 0; c < p.dN; c += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + t_lane + O_COL + c, raw);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * factor);
+                    tmem_st_32x32(tmem_base + t_lane + O_COL + c, raw);
+                }
+                tmem_st_wait();
+            }
+            // pass 2: P = exp2(x - m), row sum, fp16 P into the swizzled A tile
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + t_lane + c, raw);
+                tmem_ld_wait();
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (c + i < kv_valid) ? exp2f(__uint_as_float(raw[i]) * p.scale_log2 - m_used) : 0.0f;
+                    float p1 = (c + i + 1 < kv_valid) ? exp2f(__uint_as_float(raw[i + 1]) * p.scale_log2 - m_used) : 0.0f;
+                    l += p0 + p1;
+                    __half2 h2 = __floats2half2_rn(p0, p1);
+                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                uint8_t* sub = prow + (c >> 6) * 16384;
+                const int j0 = (c & 63) >> 3;  // first 16-byte chunk of this 32-column group inside the 128-byte row
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 u = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+                    *reinterpret_cast<uint4*>(sub + (((j0 + g) ^ sw) << 4)) = u;
+                }
+            }
+            // S consumed; P visible to the async proxy; O rescaled
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(s_empty);
+                mbar_arrive(p_full);
+            }
+        }
+        // epilogue: O / l -> fp16
+        fa_wait(o_done, (nblk - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const int row = q0 + r;
+        __half* orow = p.out + b * p.o_bs + static_cast<long long>(row) * p.ldo + head * p.d;
+        for (int c = 0; c < p.dN; c += 32) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_base + t_lane + O_COL + c, raw);
+            tmem_ld_wait();
+            if (row < p.seq_q) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (c + i + 8 <= p.d) {
+                        __half2 h0 = __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+                        __half2 h1 = __floats2half2_rn(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
+                        __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv);
+                        __half2 h3 = __floats2half2_rn(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&h0);
+                        u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2);
+                        u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(orow + c + i) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
+}
+
+template <int DCH, int KV_STAGES>
+static int launch_flash(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashParams& p,
+                        cudaStream_t st) {
+    constexpr int SMEM = DCH * 16384 * (1 + 2 * KV_STAGES) + 2 * 16384 + (5 + 4 * KV_STAGES) * 8 + 16 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(flash_attn_kernel<DCH, KV_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+            cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    dim3 grid((p.seq_q + 127) / 128, p.heads, p.batch);
+    flash_attn_kernel<DCH, KV_STAGES><<<grid, 192, SMEM, st>>>(mq, mk, mv, p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static char g_fa_err[256] = "";
+const char* flash_last_error() { return g_fa_err; }
+
+int flash_attn_setup(FlashOp* op, const __half* q, const __half* k, const __half* v, int ld, long long bs, __half* out,
+                     int ldo, long long o_bs, int seq, int heads, int d, int batch) {
+    if ((d % 8) != 0 || d > 192 || (ld % 8) != 0) {
+        snprintf(g_fa_err, sizeof(g_fa_err), "flash attention: unsupported head dim %d / row stride %d", d, ld);
+        return -1;
+    }
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)seq, (uint64_t)heads, (uint64_t)batch};
+    uint64_t st[3] = {(uint64_t)ld * 2, (uint64_t)d * 2, (uint64_t)bs * 2};
+    if (batch == 1) st[2] = (uint64_t)ld * 2 * seq;
+    uint32_t box[4] = {64, 128, 1, 1};
+    if (make_map_4d(&op->mq, q, dims, st, box) || make_map_4d(&op->mk, k, dims, st, box) ||
+        make_map_4d(&op->mv, v, dims, st, box)) {
+        snprintf(g_fa_err, sizeof(g_fa_err), "flash attention tensor map: %s", gemm_last_error());
+        return -1;
+    }
+    op->seq = seq;
+    op->heads = heads;
+    op->d = d;
+    op->batch = batch;
+    op->out = out;
+    op->ldo = ldo;
+    op->o_bs = o_bs;
+    return 0;
+}
+
+int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
+    FlashParams p;
+    p.seq_q = p.seq_kv = op->seq;
+    p.heads = op->heads;
+    p.batch = op->batch;
+    p.d = op->d;
+    p.dN = (op->d + 15) / 16 * 16;
+    p.ksteps_qk = (op->d + 15) / 16;
+    p.scale_log2 = (1.0f / sqrtf(static_cast<float>(op->d))) * 1.4426950408889634f;
+    p.out = op->out;
+    p.ldo = op->ldo;
+    p.o_bs = op->o_bs;
+    int r;
+    if (op->d <= 64)
+        r = launch_flash<1, 2>(op->mq, op->mk, op->mv, p, st);
+    else if (op->d <= 128)
+        r = launch_flash<2, 2>(op->mq, op->mk, op->mv, p, st);
+    else
+        r = launch_flash<3, 1>(op->mq, op->mk, op->mv, p, st);
+    if (r) snprintf(g_fa_err, sizeof(g_fa_err), "flash attention launch: %s", cudaGetErrorString(cudaGetLastError()));
+    return r;
+}
+
+}  // namespace dtp

@@ -690,44 +690,52 @@ size_t gemm_workspace_bytes(const GemmOp* op) {
 }
 
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
-    // Cost model (cycles) of the persistent kernel: per k-block the tensor pipe needs 2*BN cycles (128 x BN x 64 MACs at
-    // 4096 MAC/clk) and the TMA feed (16 KB of A + 128*BN B of B) about 64 B/clk per SM (measured); the epilogue of a
-    // tile (~350 clk per 32-column chunk) overlaps the next tile's mainloop.
+    // Cost model (SM cycles) of the persistent kernel, searched over (BN, split-K):
+    //   per k-block the tensor pipe needs 2*BN cycles (128 x BN x 64 MACs at 4096 MAC/clk/SM) and the TMA feed
+    //   (16 KB of A + 128*BN B of B) moves ~64 B/clk per SM (measured); chip-wide the L2 -> SM fabric sustains
+    //   ~3700 B/clk (measured ~7 TB/s), which bounds kernels whose tiles re-read A / B many times;
+    //   the epilogue of a tile (~350 clk per 32 columns) overlaps the next tile's mainloop;
+    //   split-K adds an fp32 partial write + a finalize pass (launch ~2000 clk + bytes at ~2500 B/clk).
     const int kSMs = 148;
     static const int cand_k[] = {32, 64, 128, 160, 192, 256};
     static const int cand_mn[] = {64, 128, 192, 256};
     const bool mn = (flags & GEMM_B_MN) != 0;
     const int* cand = mn ? cand_mn : cand_k;
     const int ncand = mn ? 4 : 6;
-    long long best_cost = -1;
-    int best = cand[ncand - 1];
+    double best_cost = -1.0;
+    int best = cand[ncand - 1], best_sp = 1;
+    const double rows = 128.0 * mtiles;
     for (int i = 0; i < ncand; ++i) {
         const int bn = cand[i];
         if (bn >= 64 && bn - 32 >= ((N + 31) / 32) * 32) continue;  // mostly padding
         const long long gn = (N + bn - 1) / bn;
-        const long long tiles = static_cast<long long>(mtiles) * gn;
-        const long long t_mma = 2LL * bn;
-        const long long t_tma = (16384 + 128LL * bn) / 64;
-        const long long t_main = num_kb * (t_mma > t_tma ? t_mma : t_tma);
-        const long long t_epi = 300 + (bn / 32) * 350LL;
-        const long long t_tile = (t_main > t_epi ? t_main : t_epi) + 200;
-        const long long per_cta = (tiles + kSMs - 1) / kSMs;
-        const long long cost = per_cta * t_tile + t_epi;
-        if (best_cost < 0 || cost <= best_cost) {
-            best_cost = cost;
-            best = bn;
+        const double t_mma = 2.0 * bn;
+        const double t_tma = (16384.0 + 128.0 * bn) / 64.0;
+        const double t_kb = t_mma > t_tma ? t_mma : t_tma;
+        const double t_epi = 300.0 + (bn / 32) * 350.0;
+        const int max_sp = (flags & GEMM_B_MN) ? 1 : 16;
+        for (int sp = 1; sp <= max_sp; ++sp) {
+            if (sp > 1 && num_kb / sp < 4) break;
+            const long long tiles = static_cast<long long>(mtiles) * gn * sp;
+            const double kb_per = static_cast<double>(num_kb) / sp;
+            const double t_main = kb_per * t_kb;
+            const double t_epi_eff = sp > 1 ? 400.0 : t_epi;
+            const double t_tile = (t_main > t_epi_eff ? t_main : t_epi_eff) + 200.0;
+            const double per_cta = static_cast<double>((tiles + kSMs - 1) / kSMs);
+            double cost = per_cta * t_tile + t_epi_eff + 1500.0;
+            const double l2_bytes = static_cast<double>(mtiles) * gn * num_kb * (16384.0 + 128.0 * bn);
+            const double t_l2 = l2_bytes / 3700.0;
+            if (t_l2 > cost) cost = t_l2;
+            if (sp > 1) cost += 2000.0 + rows * N * 4.0 * (sp + 1) / 2500.0;
+            if (best_cost < 0 || cost < best_cost * 0.97 || (cost <= best_cost && bn > best && sp <= best_sp)) {
+                best_cost = cost;
+                best = bn;
+                best_sp = sp;
+            }
         }
     }
-    const long long tiles = static_cast<long long>(mtiles) * ((N + best - 1) / best);
-    int sp = 1;
-    if (tiles * 2 <= kSMs && num_kb >= 8) {
-        sp = static_cast<int>(kSMs / tiles);
-        if (sp > num_kb / 4) sp = num_kb / 4;
-        if (sp > 16) sp = 16;
-        if (sp < 1) sp = 1;
-    }
     *BN = best;
-    *splits = sp;
+    *splits = best_sp;
 }
 
 static int num_sms() {

@@ -2,6 +2,7 @@
 // Activations are NHWC fp16 (rows = pixels, row length = channels); latents / images at the boundary are NCHW fp32
 // exactly as the reference façade hands them over (trt_inference/inpaint_pipeline.py:52-153).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -29,6 +30,20 @@ int launch_softmax_rows(__half* x, long long rows, int cols, int ld, cudaStream_
 int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out, int ldo,
                       int nq, int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
                       const int* kv_index, float scale, cudaStream_t st);
+
+// tcgen05 flash self-attention over packed rows: q/k/v point at the first head's columns, row stride ld, samples bs
+// elements apart; out[b][row][head*d + c]. Head dim d % 8 == 0, d <= 192.
+struct FlashOp {
+    CUtensorMap mq, mk, mv;
+    int seq, heads, d, batch;
+    __half* out;
+    int ldo;
+    long long o_bs;
+};
+int flash_attn_setup(FlashOp* op, const __half* q, const __half* k, const __half* v, int ld, long long bs, __half* out,
+                     int ldo, long long o_bs, int seq, int heads, int d, int batch);
+int flash_attn_launch(const FlashOp* op, cudaStream_t st);
+const char* flash_last_error();
 
 int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* out, cudaStream_t st);
 // stride-2 3x3 gather: out[(n,oy,ox)][tap*C + c] = x[n, 2*oy+ky-pad_lo, 2*ox+kx-pad_lo, c] (0 outside)

@@ -345,6 +345,23 @@ struct Builder {
             fail("indexed key/value batches are only supported for short sequences");
             return;
         }
+        if (d <= 192 && (d % 8) == 0 && nq == nkv && ldq == ldk && ldk == ldv && q_bs == kv_bs && e.opt_flash_) {
+            // tcgen05 flash attention: scores stay in TMEM
+            FlashOp fop;
+            if (flash_attn_setup(&fop, q, k, v, ldq, q_bs, out, ldo, o_bs, nq, heads, d, batch)) {
+                fail(flash_last_error());
+                return;
+            }
+            plan.add(K_FLASH, [fop, eng](cudaStream_t st) -> int {
+                if (flash_attn_launch(&fop, st)) {
+                    eng->err_ = flash_last_error();
+                    return -1;
+                }
+                return 1;
+            }, "flash_attn seq=" + std::to_string(nq) + " heads=" + std::to_string(heads) + " d=" + std::to_string(d) +
+                   " batch=" + std::to_string(batch));
+            return;
+        }
         // scores = scale * Q K^T (fp16, materialised), row softmax, out = P V with V consumed MN-major
         const long long srows = static_cast<long long>(batch) * heads * nq;
         const int ldS = (nkv + 7) & ~7;
@@ -1535,6 +1552,11 @@ int Engine::set_option(const char* name, int value) {
     const std::string n = name ? name : "";
     if (n == "sync_check") {
         opt_sync_check_ = value;
+        return 0;
+    }
+    if (n == "flash") {
+        opt_flash_ = value;
+        unet_plan_.clear();
         return 0;
     }
     if (n == "profile") {

@@ -61,7 +61,7 @@ struct Act {  // NHWC fp16 activation: rows = N*H*W pixels, C channels
     size_t bytes() const { return static_cast<size_t>(rows()) * C * sizeof(__half); }
 };
 
-enum OpKind { K_OTHER = 0, K_GEMM = 1, K_GROUPNORM = 2, K_LAYERNORM = 3, K_SOFTMAX = 4, K_ATTN_SMALL = 5, K_NUM = 6 };
+enum OpKind { K_OTHER = 0, K_GEMM = 1, K_GROUPNORM = 2, K_LAYERNORM = 3, K_SOFTMAX = 4, K_ATTN_SMALL = 5, K_FLASH = 6, K_NUM = 7 };
 
 // Optional per-op device timing (CUDA events on the launching stream), enabled with dtp_set_option("profile", 1).
 struct Profiler {
@@ -196,6 +196,7 @@ class Engine {
     long long launches_ = 0, stamps_ = 0;
     Profiler prof_;
     int opt_sync_check_ = 0;
+    int opt_flash_ = 1;
 };
 
 }  // namespace dtp

@@ -195,7 +195,7 @@ class Engine:
     def profile_dump(self, path: str):
         self._check(self._lib.dtp_profile_dump(self._h, path.encode()), "dtp_profile_dump")
 
-    KINDS = ("other", "contraction", "groupnorm", "layernorm", "softmax", "attn_small")
+    KINDS = ("other", "contraction", "groupnorm", "layernorm", "softmax", "attn_small", "flash_attn")
 
     def profile(self):
         """{kind: (device microseconds, launches)} accumulated since set_option('profile', 1)."""

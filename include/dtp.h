@@ -77,6 +77,10 @@ int dtp_op_softmax(void* x, long long rows, int cols, int ld, void* stream);
 int dtp_op_attn_small(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int nq,
                       int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
                       const int* kv_index, float scale, void* stream);
+/* tcgen05 flash self-attention over packed rows: q/k/v point at head 0 (row stride ld, samples bs elements apart);
+ * out[b][row][head*d + c] = softmax(q k^T / sqrt(d)) v. d % 8 == 0, d <= 192. */
+int dtp_op_flash_attn(const void* q, const void* k, const void* v, int ld, long long bs, void* out, int ldo,
+                      long long o_bs, int seq, int heads, int d, int batch, void* stream);
 int dtp_op_upsample2x(const void* x, int Nimg, int H, int W, int C, void* out, void* stream);
 int dtp_op_im2col_s2(const void* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, void* out, void* stream);
 /* eps3 (3B,chw) f32 [uncond|cond|tg]; DDIM eta=0 step with the reference's operation order */

@@ -188,6 +188,35 @@ def test_bmm_attention_pair(seq, heads, d):
     assert rel_l2(O, Oref) < 2e-3
 
 
+@pytest.mark.parametrize("seq,heads,d,batch", [(4096, 8, 40, 3), (1024, 8, 80, 3), (256, 8, 160, 3), (200, 4, 40, 2),
+                                                  (129, 2, 80, 1), (128, 1, 64, 1), (1000, 3, 192, 1), (384, 4, 16, 2),
+                                                  (2304, 8, 40, 1)])
+def test_flash_attention(seq, heads, d, batch):
+    """tcgen05 flash attention vs fp32 softmax(QK^T/sqrt(d))V on the same fp16 inputs; tolerance 3e-3 rel-L2."""
+    L = nat.lib()
+    C = heads * d
+    qkv = h(rnd(batch, seq, 3 * C))
+    out = torch.zeros(batch, seq, C, device=DEV, dtype=torch.float16)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    nat.check_op(L.dtp_op_flash_attn(nat.ptr(q), nat.ptr(k), nat.ptr(v), 3 * C, seq * 3 * C, nat.ptr(out), C, seq * C,
+                                     seq, heads, d, batch, nat.stream_ptr()), "flash_attn")
+    torch.cuda.synchronize()
+    qh = q.float().view(batch, seq, heads, d).transpose(1, 2)
+    kh = k.float().view(batch, seq, heads, d).transpose(1, 2)
+    vh = v.float().view(batch, seq, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(batch, seq, C)
+    assert rel_l2(out, ref) < 3e-3
+    # peaked scores exercise the lazy rescaling path (running max grows block after block)
+    if seq >= 256:
+        qs = (q.float() * 6).half()
+        nat.check_op(L.dtp_op_flash_attn(nat.ptr(qs), nat.ptr(k), nat.ptr(v), 3 * C, seq * 3 * C, nat.ptr(out), C,
+                                         seq * C, seq, heads, d, batch, nat.stream_ptr()), "flash_attn")
+        torch.cuda.synchronize()
+        qh = qs.float().view(batch, seq, heads, d).transpose(1, 2)
+        ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(batch, seq, C)
+        assert rel_l2(out, ref) < 3e-3
+
+
 @pytest.mark.parametrize("n,hw,c0,c1,silu", [(3, 256, 320, 0, 1), (3, 64, 1280, 640, 1), (2, 1024, 128, 0, 0),
                                              (3, 16, 640, 320, 1), (1, 4096, 512, 0, 1), (3, 1, 1280, 1280, 1)])
 def test_groupnorm(n, hw, c0, c1, silu):
