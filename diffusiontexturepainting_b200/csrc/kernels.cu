@@ -382,12 +382,93 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Short key sequences (nkv <= 16: the 14 image tokens of the cross-attention): one thread per (query row, head). K and V
+// of the head sit in shared memory (every lane of a warp reads the same key -> broadcast), scores and probabilities stay
+// in registers, q is streamed in 16-byte pieces.
+template <int NKV_MAX>
+__global__ void __launch_bounds__(128)
+    attn_tiny_kv_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, int ldk,
+                        const __half* __restrict__ v, int ldv, __half* __restrict__ out, int ldo, int nq, int nkv, int d,
+                        long long q_bs, long long kv_bs, long long o_bs, const int* __restrict__ kv_index, float scale) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* Ks = reinterpret_cast<__half*>(sm_raw);  // [nkv][d]
+    __half* Vs = Ks + nkv * d;                        // [nkv][d]
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int kvb = kv_index ? kv_index[b] : b;
+    const __half* kb = k + kvb * kv_bs + h * d;
+    const __half* vb = v + kvb * kv_bs + h * d;
+    const int dv = d >> 3;
+    for (int i = threadIdx.x; i < nkv * dv; i += blockDim.x) {
+        const int j = i / dv, c = i - j * dv;
+        reinterpret_cast<uint4*>(Ks)[i] = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * ldk) + c);
+        reinterpret_cast<uint4*>(Vs)[i] = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<long long>(j) * ldv) + c);
+    }
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nq) return;
+    const __half* qr = q + b * q_bs + static_cast<long long>(row) * ldq + h * d;
+    float s[NKV_MAX];
+#pragma unroll
+    for (int j = 0; j < NKV_MAX; ++j) s[j] = 0.0f;
+    for (int c = 0; c < dv; ++c) {
+        float qf[8];
+        unpack8(ld8(qr + c * 8), qf);
+#pragma unroll
+        for (int j = 0; j < NKV_MAX; ++j) {
+            if (j < nkv) {
+                float kf[8];
+                unpack8(*reinterpret_cast<const Half8*>(Ks + (j * dv + c) * 8), kf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s[j] = fmaf(qf[e], kf[e], s[j]);
+            }
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NKV_MAX; ++j)
+        if (j < nkv) m = fmaxf(m, s[j] * scale);
+    float l = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NKV_MAX; ++j) {
+        s[j] = (j < nkv) ? __expf(s[j] * scale - m) : 0.0f;
+        l += s[j];
+    }
+    const float inv = 1.0f / l;
+    __half* orow = out + b * o_bs + static_cast<long long>(row) * ldo + h * d;
+    for (int c = 0; c < dv; ++c) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NKV_MAX; ++j) {
+            if (j < nkv) {
+                float vf[8];
+                unpack8(*reinterpret_cast<const Half8*>(Vs + (j * dv + c) * 8), vf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(s[j], vf[e], o[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] *= inv;
+        st8(orow + c * 8, pack8(o));
+    }
+}
+
 int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* out, int ldo,
                       int nq, int nkv, int heads, int d, int batch, long long q_bs, long long kv_bs, long long o_bs,
                       const int* kv_index, float scale, cudaStream_t st) {
     if (nkv > 64 || nkv < 1 || (d & 1) || (ldk & 1) || (ldv & 1)) {
         snprintf(g_kerr, sizeof(g_kerr), "attn_small: unsupported nkv=%d d=%d", nkv, d);
         return -1;
+    }
+    if (nkv <= 16 && (d % 8) == 0 && (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0 && nq >= 64) {
+        const size_t smem_t = static_cast<size_t>(nkv) * d * 2 * 2;
+        if (smem_t <= 48 * 1024) {
+            dim3 grid_t((nq + 127) / 128, heads, batch);
+            attn_tiny_kv_kernel<16><<<grid_t, 128, smem_t, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs,
+                                                                 kv_bs, o_bs, kv_index, scale);
+            return check_launch("attn_tiny_kv");
+        }
     }
     const int kpitch = d + ((((d >> 1) & 1) == 0) ? 2 : 0);
     const size_t smem = static_cast<size_t>(nkv) * kpitch * 2 + ((static_cast<size_t>(nkv) * d + 7) & ~size_t(7)) * 2 +

@@ -208,11 +208,13 @@ def test_flash_attention(seq, heads, d, batch):
     assert rel_l2(out, ref) < 3e-3
     # peaked scores exercise the lazy rescaling path (running max grows block after block)
     if seq >= 256:
-        qs = (q.float() * 6).half()
-        nat.check_op(L.dtp_op_flash_attn(nat.ptr(qs), nat.ptr(k), nat.ptr(v), 3 * C, seq * 3 * C, nat.ptr(out), C,
+        qkv2 = qkv.clone()
+        qkv2[..., :C] = (qkv2[..., :C].float() * 6).half()
+        q, k, v = qkv2[..., :C], qkv2[..., C:2 * C], qkv2[..., 2 * C:]
+        nat.check_op(L.dtp_op_flash_attn(nat.ptr(q), nat.ptr(k), nat.ptr(v), 3 * C, seq * 3 * C, nat.ptr(out), C,
                                          seq * C, seq, heads, d, batch, nat.stream_ptr()), "flash_attn")
         torch.cuda.synchronize()
-        qh = qs.float().view(batch, seq, heads, d).transpose(1, 2)
+        qh = q.float().view(batch, seq, heads, d).transpose(1, 2)
         ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(batch, seq, C)
         assert rel_l2(out, ref) < 3e-3
 
