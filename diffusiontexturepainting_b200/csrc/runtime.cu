@@ -319,7 +319,7 @@ struct Builder {
                 return -1;
             }
             return 1;
-        });
+        }, "layernorm rows=" + std::to_string(rows) + " C=" + std::to_string(C));
     }
 
     // q/k/v given as pointers with row strides; batch entries `seq` rows apart
@@ -513,6 +513,8 @@ Engine::Engine(const dtp_config& cfg) : cfg_(cfg) {
 }
 
 Engine::~Engine() {
+    if (g_infer_.exec) cudaGraphExecDestroy(g_infer_.exec);
+    if (g_stamp_.exec) cudaGraphExecDestroy(g_stamp_.exec);
     for (auto& kv : w_)
         if (kv.second.dev) cudaFree(kv.second.dev);
     for (void* p : persistent_) cudaFree(p);
@@ -1448,14 +1450,106 @@ int Engine::ensure_io(int B, int R) {
     lat2_ = static_cast<float*>(persistent(2 * b * 4 * hw * 4, true));
     // canvas pre-process outputs: masked (3), mask (1), ctx (3), ctx mask (1), scratch (1), raw result (3), images x2 (6)
     pre_ = static_cast<float*>(persistent(b * 18 * r * r * 4, true));
-    if (!lat_ || !mask3_ || !masked3_ || !lat2_ || !pre_) return -1;
+    // staging: canvas (4), brush (3, one image), init latents, vae noise, out f32 (3); out u8 (3 bytes / pixel)
+    stage_ = static_cast<float*>(persistent((b * 7 * r * r + 3 * r * r + b * 4 * hw + 2 * b * 4 * hw) * 4, true));
+    stage_u8_ = static_cast<unsigned char*>(persistent(b * 3 * r * r, true));
+    if (!lat_ || !mask3_ || !masked3_ || !lat2_ || !pre_ || !stage_ || !stage_u8_) return -1;
+    g_infer_.key.clear();
+    g_stamp_.key.clear();
     io_cap_B_ = b;
     io_cap_R_ = r;
     return 0;
 }
 
+std::string Engine::schedule_key() const {
+    char buf[160];
+    double h = 0.0;
+    for (int i = 0; i < n_steps_; ++i) h = h * 1.000001 + ts_[i] * (i + 1) + a_t_[i] * 7.0 + a_prev_[i] * 13.0;
+    snprintf(buf, sizeof(buf), "n%d c%.9g t%.9g s%d h%.17g", n_steps_, cfg_w_, tg_w_, tg_steps_, h);
+    return buf;
+}
+
+int Engine::run_graphed(GraphSlot& slot, const std::string& key, const std::function<int(cudaStream_t)>& body,
+                        cudaStream_t st) {
+    if (!opt_graph_ || prof_.on) return body(st);
+    if (slot.key != key) {
+        if (slot.exec) cudaGraphExecDestroy(slot.exec);
+        slot.exec = nullptr;
+        slot.key = key;
+        slot.warm = 0;
+    }
+    if (slot.warm < 1) {  // first call with this key runs eagerly: builds plans, tables, kernel attributes
+        ++slot.warm;
+        return body(st);
+    }
+    if (!slot.exec) {
+        const long long before = launches_;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return body(st);
+        }
+        const int rc = body(st);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc != 0 || e != cudaSuccess || g == nullptr) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            if (rc != 0) return rc;
+            return fail(std::string("graph capture failed: ") + cudaGetErrorString(e));
+        }
+        slot.launches = launches_ - before;
+        launches_ = before;
+        if (cudaGraphInstantiate(&slot.exec, g, 0) != cudaSuccess) {
+            cudaGraphDestroy(g);
+            slot.exec = nullptr;
+            return fail("cudaGraphInstantiate failed");
+        }
+        cudaGraphDestroy(g);
+    }
+    if (cudaGraphLaunch(slot.exec, st) != cudaSuccess) return fail("cudaGraphLaunch failed");
+    launches_ += slot.launches;
+    ++graph_launches_;
+    return 0;
+}
+
 int Engine::infer(int B, int R, const float* masked_img, const float* mask, const float* ctx_img, const float* ctx_mask,
                   const float* init_latents, const float* vae_noise, float* out_images, cudaStream_t st) {
+    if (B < 1 || R < 8 || (R % 8)) return fail("infer: bad batch / resolution");
+    if (!finalized_ && finalize_weights()) return -1;
+    if (!cond_set_) return fail("infer: call dtp_set_condition first");
+    if (ensure_io(B, R)) return -1;
+    if (!opt_graph_ || prof_.on)
+        return infer_body(B, R, masked_img, mask, ctx_img, ctx_mask, init_latents, vae_noise, out_images, st);
+    // stage the caller's tensors at fixed addresses so the captured graph can be replayed
+    const size_t plane = static_cast<size_t>(B) * R * R, hw = static_cast<size_t>(R / 8) * (R / 8);
+    float* s_masked = pre_;
+    float* s_mask = pre_ + 3 * plane;
+    float* s_ctx = pre_ + 4 * plane;
+    float* s_cmask = pre_ + 7 * plane;
+    float* s_out = pre_ + 9 * plane;
+    float* s_lat = stage_ + 7 * plane + 3 * static_cast<size_t>(R) * R;
+    float* s_noise = s_lat + static_cast<size_t>(B) * 4 * hw;
+    cudaMemcpyAsync(s_masked, masked_img, 3 * plane * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_mask, mask, plane * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_ctx, ctx_img, 3 * plane * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_cmask, ctx_mask, plane * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_lat, init_latents, static_cast<size_t>(B) * 4 * hw * 4, cudaMemcpyDeviceToDevice, st);
+    if (vae_noise) cudaMemcpyAsync(s_noise, vae_noise, static_cast<size_t>(2) * B * 4 * hw * 4, cudaMemcpyDeviceToDevice, st);
+    const std::string key = "i B" + std::to_string(B) + " R" + std::to_string(R) + (vae_noise ? " n1 " : " n0 ") +
+                            schedule_key();
+    const float* nz = vae_noise ? s_noise : nullptr;
+    if (run_graphed(g_infer_, key,
+                    [=](cudaStream_t s) { return infer_body(B, R, s_masked, s_mask, s_ctx, s_cmask, s_lat, nz, s_out, s); },
+                    st))
+        return -1;
+    if (cudaMemcpyAsync(out_images, s_out, 3 * plane * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("infer: output copy failed");
+    return 0;
+}
+
+int Engine::infer_body(int B, int R, const float* masked_img, const float* mask, const float* ctx_img,
+                       const float* ctx_mask, const float* init_latents, const float* vae_noise, float* out_images,
+                       cudaStream_t st) {
     if (B < 1 || R < 8 || (R % 8)) return fail("infer: bad batch / resolution");
     if (!finalized_ && finalize_weights()) return -1;
     if (!cond_set_) return fail("infer: call dtp_set_condition first");
@@ -1491,6 +1585,41 @@ int Engine::infer(int B, int R, const float* masked_img, const float* mask, cons
 int Engine::stamp(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
                   const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st) {
     if (B < 1 || R < 8 || (R % 8)) return fail("stamp: bad batch / resolution");
+    if (!finalized_ && finalize_weights()) return -1;
+    if (!cond_set_) return fail("stamp: call dtp_set_condition first");
+    if (ensure_io(B, R)) return -1;
+    if (!opt_graph_ || prof_.on)
+        return stamp_body(B, R, canvas, brush, pad, init_latents, vae_noise, composite, out_f32, out_u8, st);
+    const size_t plane = static_cast<size_t>(B) * R * R, hw = static_cast<size_t>(R / 8) * (R / 8);
+    float* s_canvas = stage_;
+    float* s_out = stage_ + 4 * plane;
+    float* s_brush = stage_ + 7 * plane;
+    float* s_lat = s_brush + 3 * static_cast<size_t>(R) * R;
+    float* s_noise = s_lat + static_cast<size_t>(B) * 4 * hw;
+    cudaMemcpyAsync(s_canvas, canvas, 4 * plane * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_brush, brush, static_cast<size_t>(3) * R * R * 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s_lat, init_latents, static_cast<size_t>(B) * 4 * hw * 4, cudaMemcpyDeviceToDevice, st);
+    if (vae_noise) cudaMemcpyAsync(s_noise, vae_noise, static_cast<size_t>(2) * B * 4 * hw * 4, cudaMemcpyDeviceToDevice, st);
+    const std::string key = "s B" + std::to_string(B) + " R" + std::to_string(R) + " p" + std::to_string(pad) +
+                            (vae_noise ? " n1" : " n0") + (composite ? " c1" : " c0") + (out_f32 ? " f1" : " f0") +
+                            (out_u8 ? " u1 " : " u0 ") + schedule_key();
+    const float* nz = vae_noise ? s_noise : nullptr;
+    float* of = out_f32 ? s_out : nullptr;
+    unsigned char* ou = out_u8 ? stage_u8_ : nullptr;
+    if (run_graphed(g_stamp_, key,
+                    [=](cudaStream_t s) { return stamp_body(B, R, s_canvas, s_brush, pad, s_lat, nz, composite, of, ou, s); },
+                    st))
+        return -1;
+    if (out_f32 && cudaMemcpyAsync(out_f32, s_out, 3 * plane * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("stamp: output copy failed");
+    if (out_u8 && cudaMemcpyAsync(out_u8, stage_u8_, 3 * plane, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return fail("stamp: output copy failed");
+    return 0;
+}
+
+int Engine::stamp_body(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+                       const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st) {
+    if (B < 1 || R < 8 || (R % 8)) return fail("stamp: bad batch / resolution");
     if (ensure_io(B, R)) return -1;
     const size_t plane = static_cast<size_t>(B) * R * R;
     float* masked = pre_;
@@ -1505,7 +1634,7 @@ int Engine::stamp(int B, int R, const float* canvas, const float* brush, int pad
     }
     launches_ += 2;
     float* dst = (composite || out_f32 == nullptr) ? raw : out_f32;
-    if (infer(B, R, masked, mask, ctx, cmask, init_latents, vae_noise, dst, st)) return -1;
+    if (infer_body(B, R, masked, mask, ctx, cmask, init_latents, vae_noise, dst, st)) return -1;
     if (composite || out_u8) {
         if (composite) {
             KCHECK(launch_composite(canvas, raw, B, R, out_f32, out_u8, st));
@@ -1522,6 +1651,7 @@ long long Engine::counter(const char* name) const {
     if (n == "stamps") return stamps_;
     if (n == "arena_peak") return static_cast<long long>(arena_.peak());
     if (n == "arena_bytes") return static_cast<long long>(cfg_.arena_bytes);
+    if (n == "graph_launches") return graph_launches_;
     if (n == "unet_plan_ops") return static_cast<long long>(unet_plan_.ops.size());
     if (n == "ws_bytes") return static_cast<long long>(ws_bytes_);
     if (n.rfind("prof_us_", 0) == 0 || n.rfind("prof_n_", 0) == 0) {
@@ -1554,9 +1684,15 @@ int Engine::set_option(const char* name, int value) {
         opt_sync_check_ = value;
         return 0;
     }
+    if (n == "graph") {
+        opt_graph_ = value;
+        return 0;
+    }
     if (n == "flash") {
         opt_flash_ = value;
         unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
         return 0;
     }
     if (n == "profile") {

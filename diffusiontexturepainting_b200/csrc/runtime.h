@@ -116,6 +116,11 @@ class Engine {
               const float* init_latents, const float* vae_noise, float* out_images, cudaStream_t st);
     int stamp(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
               const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st);
+    int infer_body(int B, int R, const float* masked_img, const float* mask, const float* ctx_img,
+                   const float* ctx_mask, const float* init_latents, const float* vae_noise, float* out_images,
+                   cudaStream_t st);
+    int stamp_body(int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
+                   const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, cudaStream_t st);
     int vae_encode(int Nb, int R, const float* images, const float* noise, float* latents_out, cudaStream_t st);
     int vae_decode(int B, int R, const float* latents, float* images_out, cudaStream_t st);
     int unet_forward(int B, int R, const float* sample, const float* latents, const float* mask3, const float* masked3,
@@ -192,6 +197,22 @@ class Engine {
     std::vector<std::pair<std::string, int>> resnets_;  // UNet resnet prefix -> offset into the temb row
     int cur_step_ = 0;
     bool temb_dirty_ = true;
+
+    // CUDA-graph replay of a whole stamp (all launches of pre-process, 2x VAE encode, N UNet evaluations, decode)
+    struct GraphSlot {
+        std::string key;
+        cudaGraphExec_t exec = nullptr;
+        int warm = 0;
+        long long launches = 0;
+    };
+    GraphSlot g_infer_, g_stamp_;
+    int run_graphed(GraphSlot& slot, const std::string& key, const std::function<int(cudaStream_t)>& body,
+                    cudaStream_t st);
+    std::string schedule_key() const;
+    float* stage_ = nullptr;           // fixed-address staging of caller inputs / outputs for graph replay
+    unsigned char* stage_u8_ = nullptr;
+    int opt_graph_ = 1;
+    long long graph_launches_ = 0;
 
     long long launches_ = 0, stamps_ = 0;
     Profiler prof_;
