@@ -105,8 +105,7 @@ int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const v
 
 int dtp_op_groupnorm(const void* x0, int C0, const void* x1, int C1, int Nimg, int HW, int groups, const float* gamma,
                      const float* beta, float eps, int silu, void* out, void* stream) {
-    const int chunks = gn_num_chunks(HW, C0 + C1);
-    if (ensure_ws(sizeof(float) * 2 * groups * chunks * Nimg)) return -1;
+    if (ensure_ws(sizeof(float) * gn_ws_floats(Nimg, HW, C0 + C1, groups))) return -1;
     return launch_groupnorm((const __half*)x0, C0, (const __half*)x1, C1, Nimg, HW, groups, gamma, beta, eps, silu,
                             (__half*)out, g_ws, (cudaStream_t)stream);
 }

@@ -36,6 +36,11 @@ __device__ __forceinline__ void fa_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000LL) __trap();
     }
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // DCH: 64-wide chunks of the (padded) head dim; KV_STAGES: ring depth of the K and V tiles
@@ -165,24 +170,36 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
-        float m_used = -INFINITY, l = 0.0f;
+        float m_used = -INFINITY, l = 0.0f;  // m_used in the log2 domain (score * scale * log2 e)
         uint8_t* prow = sP + r * 128;
         const int sw = r & 7;
+        const float sc = p.scale_log2;
         for (int j = 0; j < nblk; ++j) {
             fa_wait(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = min(128, p.seq_kv - j * 128);
-            // pass 1: block maximum of the scaled scores
+            // pass 1: block maximum of the raw scores (four 32-column TMEM reads in flight together)
             float bm = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_base + t_lane + c, raw);
+            {
+                uint32_t a[32], b[32];
+                tmem_ld_32x32(tmem_base + t_lane + 0, a);
+                tmem_ld_32x32(tmem_base + t_lane + 32, b);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < kv_valid) bm = fmaxf(bm, __uint_as_float(raw[i]) * p.scale_log2);
+                for (int i = 0; i < 32; ++i) {
+                    if (i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
+                    if (32 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(b[i]));
+                }
+                tmem_ld_32x32(tmem_base + t_lane + 64, a);
+                tmem_ld_32x32(tmem_base + t_lane + 96, b);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (64 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
+                    if (96 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(b[i]));
+                }
             }
+            bm *= sc;  // scale > 0: max commutes with the scaling
             // P (smem) and O (TMEM) are free once the previous block's second MMA has retired
             if (j > 0) fa_wait(o_done, (j - 1) & 1);
             tc_fence_after();
@@ -192,52 +209,63 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
                 m_used = bm;
             } else if (bm > m_used + 8.0f) {
                 need = true;
-                factor = exp2f(m_used - bm);
+                factor = ex2_approx(m_used - bm);
                 m_used = bm;
             }
             if (__any_sync(0xffffffffu, need)) {
                 l *= factor;
                 for (int c = 0; c < p.dN; c += 32) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(tmem_base + t_lane + O_COL + c, raw);
+                    uint32_t o[32];
+                    tmem_ld_32x32(tmem_base + t_lane + O_COL + c, o);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * factor);
-                    tmem_st_32x32(tmem_base + t_lane + O_COL + c, raw);
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st_32x32(tmem_base + t_lane + O_COL + c, o);
                 }
                 tmem_st_wait();
             }
-            // pass 2: P = exp2(x - m), row sum, fp16 P into the swizzled A tile
+            // pass 2: P = exp2(s * scale - m): one FFMA + one MUFU per element; fp16 P into the swizzled A tile
+            const float neg_m = -m_used;
+            float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_base + t_lane + c, raw);
+            for (int hc = 0; hc < 128; hc += 64) {
+                uint32_t raw[64];
+                tmem_ld_32x32(tmem_base + t_lane + hc, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+                tmem_ld_32x32(tmem_base + t_lane + hc + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
                 tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c + i < kv_valid) ? exp2f(__uint_as_float(raw[i]) * p.scale_log2 - m_used) : 0.0f;
-                    float p1 = (c + i + 1 < kv_valid) ? exp2f(__uint_as_float(raw[i + 1]) * p.scale_log2 - m_used) : 0.0f;
-                    l += p0 + p1;
-                    __half2 h2 = __floats2half2_rn(p0, p1);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+                if (hc == 64) {
+                    // the score tile is fully in registers: release S to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_empty);
                 }
-                uint8_t* sub = prow + (c >> 6) * 16384;
-                const int j0 = (c & 63) >> 3;  // first 16-byte chunk of this 32-column group inside the 128-byte row
+                uint8_t* sub = prow + (hc >> 6) * 16384;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 u = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-                    *reinterpret_cast<uint4*>(sub + (((j0 + g) ^ sw) << 4)) = u;
+                for (int c = 0; c < 64; c += 8) {
+                    float e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
+                        if (hc + c + i >= kv_valid) e[i] = 0.0f;
+                    }
+                    l0 += (e[0] + e[1]) + (e[2] + e[3]);
+                    l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                    __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
+                    __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h0);
+                    u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    u.z = *reinterpret_cast<uint32_t*>(&h2);
+                    u.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(sub + (((c >> 3) ^ sw) << 4)) = u;
                 }
             }
-            // S consumed; P visible to the async proxy; O rescaled
+            l += l0 + l1;
+            // P visible to the async proxy; O rescaled
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(s_empty);
-                mbar_arrive(p_full);
-            }
+            if (lane == 0) mbar_arrive(p_full);
         }
         // epilogue: O / l -> fp16
         fa_wait(o_done, (nblk - 1) & 1);
@@ -332,7 +360,7 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
     p.o_bs = op->o_bs;
     int r;
     if (op->d <= 64)
-        r = launch_flash<1, 2>(op->mq, op->mk, op->mv, p, st);
+        r = launch_flash<1, 1>(op->mq, op->mk, op->mv, p, st);
     else if (op->d <= 128)
         r = launch_flash<2, 2>(op->mq, op->mk, op->mv, p, st);
     else

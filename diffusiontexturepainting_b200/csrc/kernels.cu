@@ -46,7 +46,10 @@ __device__ __forceinline__ Half8 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm: (1) per-chunk partial sums, (2) finalize mean / rstd in double, (3) apply (+SiLU)
+// GroupNorm (+SiLU) over one or two NHWC sources.
+//   large tensors: (1) per-chunk partial sums; the last CTA of a sample (ticket counter) reduces them in a fixed order in
+//                  double and emits per-channel (scale, shift); (2) apply.          -> 2 launches, deterministic
+//   small tensors: one CTA per (sample, group) keeps its elements in registers: stats + apply in a single launch.
 // ------------------------------------------------------------------------------------------------------------
 int gn_num_chunks(int HW, int C) {
     long long elems = static_cast<long long>(HW) * C;
@@ -57,13 +60,33 @@ int gn_num_chunks(int HW, int C) {
     return static_cast<int>(chunks);
 }
 size_t gn_ws_floats(int Nimg, int HW, int C, int groups) {
-    return static_cast<size_t>(Nimg) * gn_num_chunks(HW, C) * groups * 2 + static_cast<size_t>(Nimg) * groups * 2;
+    return static_cast<size_t>(Nimg) * gn_num_chunks(HW, C) * groups * 2 + static_cast<size_t>(Nimg) * C * 2 + 64;
+}
+
+static int* g_gn_counters = nullptr;  // self-resetting per-sample tickets (stream-ordered reuse)
+static int gn_counters(int Nimg, int** out) {
+    static int cap = 0;
+    if (Nimg > cap) {
+        if (g_gn_counters) cudaFree(g_gn_counters);
+        cap = Nimg < 256 ? 256 : Nimg;
+        if (cudaMalloc(&g_gn_counters, cap * sizeof(int)) != cudaSuccess) {
+            cap = 0;
+            g_gn_counters = nullptr;
+            return -1;
+        }
+        cudaMemset(g_gn_counters, 0, cap * sizeof(int));
+    }
+    *out = g_gn_counters;
+    return 0;
 }
 
 // grid (chunks, Nimg); block = CV * rows_per_iter threads, CV = C / 8
 __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
-                                int groups, int chunks, float* __restrict__ partial) {
+                                int groups, int chunks, float* __restrict__ partial, int* __restrict__ counters,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                float* __restrict__ coef) {
     extern __shared__ float2 sm_acc[];  // [rows_per_iter][C]
+    __shared__ int s_ticket;
     const int C = C0 + C1;
     const int CV = C >> 3;
     const int cv = threadIdx.x % CV;
@@ -98,8 +121,8 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
 #pragma unroll
     for (int e = 0; e < 8; ++e) sm_acc[prow * C + c + e] = make_float2(s[e], ss[e]);
     __syncthreads();
+    const int cpg = C / groups;
     if (threadIdx.x < groups) {
-        const int cpg = C / groups;
         float a = 0.0f, b = 0.0f;
         for (int r = 0; r < rows_per_iter; ++r)
             for (int cc = 0; cc < cpg; ++cc) {
@@ -111,30 +134,41 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
         dst[0] = a;
         dst[1] = b;
     }
-}
-
-// grid Nimg; block groups
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int groups, double count, float eps,
-                                   float* __restrict__ stats) {
-    const int n = blockIdx.x, g = threadIdx.x;
-    if (g >= groups) return;
-    double a = 0.0, b = 0.0;
-    for (int ch = 0; ch < chunks; ++ch) {
-        const float* src = partial + ((static_cast<long long>(n) * chunks + ch) * groups + g) * 2;
-        a += static_cast<double>(src[0]);
-        b += static_cast<double>(src[1]);
+    // last CTA of this sample folds the partials (fixed order -> bitwise reproducible) into per-channel scale / shift
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&counters[n], 1);
+    __syncthreads();
+    if (s_ticket != chunks - 1) return;
+    __threadfence();
+    float* stat = reinterpret_cast<float*>(sm_acc);  // [groups][2] mean, rstd
+    if (threadIdx.x < groups) {
+        double a = 0.0, b = 0.0;
+        const volatile float* pp = partial + (static_cast<long long>(n) * chunks * groups + threadIdx.x) * 2;
+        for (int ch = 0; ch < chunks; ++ch) {
+            a += static_cast<double>(pp[static_cast<long long>(ch) * groups * 2]);
+            b += static_cast<double>(pp[static_cast<long long>(ch) * groups * 2 + 1]);
+        }
+        const double count = static_cast<double>(HW) * cpg;
+        const double mean = a / count;
+        double var = b / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        stat[2 * threadIdx.x] = static_cast<float>(mean);
+        stat[2 * threadIdx.x + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     }
-    const double mean = a / count;
-    double var = b / count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[(n * groups + g) * 2] = static_cast<float>(mean);
-    stats[(n * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const int g = ch / cpg;
+        const float sc = stat[2 * g + 1] * __ldg(gamma + ch);
+        coef[(static_cast<long long>(n) * C + ch) * 2] = sc;
+        coef[(static_cast<long long>(n) * C + ch) * 2 + 1] = __ldg(beta + ch) - stat[2 * g] * sc;
+    }
+    if (threadIdx.x == 0) counters[n] = 0;
 }
 
 __global__ void __launch_bounds__(256)
-    gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
-                    long long total_vec, const float* __restrict__ stats, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, int silu, __half* __restrict__ out) {
+    gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
+                    long long total_vec, const float* __restrict__ coef, int silu, __half* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total_vec) return;
     const int C = C0 + C1;
@@ -143,22 +177,98 @@ __global__ void __launch_bounds__(256)
     const long long pix = i / CV;  // n*HW + p
     const int n = static_cast<int>(pix / HW);
     const int c = cv * 8;
-    const int cpg = C / groups;
     float f[8];
     if (c < C0)
         unpack8(ld8(x0 + pix * C0 + c), f);
     else
         unpack8(ld8(x1 + pix * C1 + (c - C0)), f);
+    const float4* cf = reinterpret_cast<const float4*>(coef + (static_cast<long long>(n) * C + c) * 2);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int g = (c + e) / cpg;
-        const float mean = __ldg(stats + (n * groups + g) * 2);
-        const float rstd = __ldg(stats + (n * groups + g) * 2 + 1);
-        float y = (f[e] - mean) * rstd * __ldg(gamma + c + e) + __ldg(beta + c + e);
-        if (silu) y = silu_f(y);
-        f[e] = y;
+    for (int e = 0; e < 4; ++e) {
+        const float4 t = __ldg(cf + e);  // (scale, shift) of two channels
+        float y0 = fmaf(f[2 * e], t.x, t.y), y1 = fmaf(f[2 * e + 1], t.z, t.w);
+        if (silu) {
+            y0 = silu_f(y0);
+            y1 = silu_f(y1);
+        }
+        f[2 * e] = y0;
+        f[2 * e + 1] = y1;
     }
     st8(out + pix * C + c, pack8(f));
+}
+
+// one CTA per (group, sample); every thread keeps up to EPT half2 pairs of the group's HW x cpg elements in registers
+template <int EPT>
+__global__ void __launch_bounds__(256)
+    gn_group_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                    __half* __restrict__ out) {
+    __shared__ float red[2][8];
+    __shared__ float s_mean, s_rstd;
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int hp = cpg >> 1;           // half2 pairs per pixel
+    const int total = HW * hp;         // pairs in this group
+    const int c_base = g * cpg;
+    float2 v[EPT];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        v[k] = make_float2(0.0f, 0.0f);
+        if (i < total) {
+            const int p = i / hp, c = c_base + 2 * (i - p * hp);
+            const __half* src = (c < C0) ? x0 + (static_cast<long long>(n) * HW + p) * C0 + c
+                                         : x1 + (static_cast<long long>(n) * HW + p) * C1 + (c - C0);
+            v[k] = __half22float2(*reinterpret_cast<const __half2*>(src));
+            s += v[k].x + v[k].y;
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += red[0][w];
+        s_mean = t / static_cast<float>(2 * total);
+    }
+    __syncthreads();
+    const float mean = s_mean;
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < total) {
+            const float a = v[k].x - mean, b = v[k].y - mean;
+            ss += a * a + b * b;
+        }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[1][warp] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += red[1][w];
+        s_rstd = rsqrtf(t / static_cast<float>(2 * total) + eps);
+    }
+    __syncthreads();
+    const float rstd = s_rstd;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < total) {
+            const int p = i / hp, c = c_base + 2 * (i - p * hp);
+            float y0 = (v[k].x - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+            float y1 = (v[k].y - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+            if (silu) {
+                y0 = silu_f(y0);
+                y1 = silu_f(y1);
+            }
+            *reinterpret_cast<__half2*>(out + (static_cast<long long>(n) * HW + p) * C + c) = __floats2half2_rn(y0, y1);
+        }
+    }
 }
 
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
@@ -175,6 +285,18 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         snprintf(g_kerr, sizeof(g_kerr), "groupnorm: C=%d too large", C);
         return -1;
     }
+    const int cpg = C / groups;
+    const long long pairs = static_cast<long long>(HW) * (cpg / 2);
+    if ((cpg % 2) == 0 && pairs <= 256 * 32) {
+        dim3 grid(groups, Nimg);
+        if (pairs <= 256 * 4)
+            gn_group_kernel<4><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+        else if (pairs <= 256 * 12)
+            gn_group_kernel<12><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+        else
+            gn_group_kernel<32><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+        return check_launch("gn_group");
+    }
     const int chunks = gn_num_chunks(HW, C);
     int rows_per_iter = 256 / CV;
     if (rows_per_iter < 1) rows_per_iter = 1;
@@ -183,17 +305,21 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         rows_per_iter = (groups + CV - 1) / CV;
         threads = CV * rows_per_iter;
     }
+    int* counters = nullptr;
+    if (gn_counters(Nimg, &counters)) {
+        snprintf(g_kerr, sizeof(g_kerr), "groupnorm: counter allocation failed");
+        return -1;
+    }
     float* partial = stats_ws;
-    float* stats = stats_ws + static_cast<size_t>(Nimg) * chunks * groups * 2;
-    const size_t smem = static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
-    gn_stats_kernel<<<dim3(chunks, Nimg), threads, smem, st>>>(x0, C0, x1, C1, HW, groups, chunks, partial);
+    float* coef = stats_ws + ((static_cast<size_t>(Nimg) * chunks * groups * 2 + 3) & ~size_t(3));
+    size_t smem = static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
+    if (smem < static_cast<size_t>(groups) * 8) smem = static_cast<size_t>(groups) * 8;
+    gn_stats_kernel<<<dim3(chunks, Nimg), threads, smem, st>>>(x0, C0, x1, C1, HW, groups, chunks, partial, counters,
+                                                               gamma, beta, eps, coef);
     if (check_launch("gn_stats")) return -1;
-    gn_finalize_kernel<<<Nimg, ((groups + 31) / 32) * 32, 0, st>>>(partial, chunks, groups,
-                                                                    static_cast<double>(HW) * (C / groups), eps, stats);
-    if (check_launch("gn_finalize")) return -1;
     const long long total_vec = static_cast<long long>(Nimg) * HW * CV;
-    gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, st>>>(x0, C0, x1, C1, HW, groups, total_vec,
-                                                                                   stats, gamma, beta, silu, out);
+    gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, st>>>(x0, C0, x1, C1, HW, total_vec, coef,
+                                                                                   silu, out);
     return check_launch("gn_apply");
 }
 

@@ -299,7 +299,7 @@ struct Builder {
                 eng->err_ = kernels_last_error();
                 return -1;
             }
-            return 3;
+            return 2;
         }, "groupnorm rows=" + std::to_string(static_cast<long long>(Nimg) * HW) + " C=" + std::to_string(C0 + C1));
         release_raw(ws);  // stream-ordered: the next consumer of this slab runs after the norm
         return out;

@@ -220,7 +220,9 @@ def test_flash_attention(seq, heads, d, batch):
 
 
 @pytest.mark.parametrize("n,hw,c0,c1,silu", [(3, 256, 320, 0, 1), (3, 64, 1280, 640, 1), (2, 1024, 128, 0, 0),
-                                             (3, 16, 640, 320, 1), (1, 4096, 512, 0, 1), (3, 1, 1280, 1280, 1)])
+                                             (3, 16, 640, 320, 1), (1, 4096, 512, 0, 1), (3, 1, 1280, 1280, 1),
+                                             (3, 4096, 320, 0, 1), (3, 4096, 640, 320, 1), (2, 1024, 1280, 640, 0),
+                                             (2, 16384, 128, 0, 1)])
 def test_groupnorm(n, hw, c0, c1, silu):
     L = nat.lib()
     x0 = h(rnd(n, hw, c0) * 2 + 0.5)
