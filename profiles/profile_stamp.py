@@ -21,6 +21,7 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--tag", default="r1")
 ap.add_argument("--stamps", type=int, default=1)
 ap.add_argument("--no-op-profile", action="store_true")
+ap.add_argument("--no-graph", action="store_true")
 a = ap.parse_args()
 R, S, B = a.resolution, a.denoise_steps, a.batch
 model = TRTConditionalInpainter(R, device=0, model_config=W.sd15_config(), max_batch_size=B)
@@ -32,6 +33,8 @@ model.pipeline.update_infer_settings(S, 2.0, 1.0, S)
 model.pipeline._push_schedule(1.0)
 out = torch.empty(B, 3, R, R, device="cuda")
 eng = model.engine
+if a.no_graph:
+    eng.set_option("graph", 0)
 eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
 torch.cuda.synchronize()
 if not a.no_op_profile:
