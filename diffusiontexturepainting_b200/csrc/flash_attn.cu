@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
     const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
     const int nblk = (p.seq_kv + 127) / 128;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapQ);
         tma_prefetch_desc(&mapK);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // q / k / v are produced by the preceding projection kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -314,7 +316,7 @@ static int launch_flash(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
         attr_set = true;
     }
     dim3 grid((p.seq_q + 127) / 128, p.heads, p.batch);
-    flash_attn_kernel<DCH, KV_STAGES><<<grid, 192, SMEM, st>>>(mq, mk, mv, p);
+    launch_k(flash_attn_kernel<DCH, KV_STAGES>, dim3(grid), dim3(192), SMEM, st, mq, mk, mv, p);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

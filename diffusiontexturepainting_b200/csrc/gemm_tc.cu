@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(192, 1)
     const bool b_mn = (p.flags & GEMM_B_MN) != 0;
     const int total_tiles = p.total_tiles;
 
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue now
     if (threadIdx.x == 0) DBG_MARK(0);
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
@@ -266,15 +267,31 @@ __global__ void __launch_bounds__(192, 1)
             const uint32_t b_bytes = b_mn ? static_cast<uint32_t>(B_CHUNKS) * 8192u : B_BYTES;
             int stage = 0;
             uint32_t phase = 0;
+            // Weights (the B operand of linear / conv problems) are never written by a kernel of the stream: their first
+            // STAGES tiles are requested BEFORE waiting for the predecessor kernel, hiding the DRAM latency of
+            // weight-streaming layers behind the previous kernel's tail. Activations (A) are only touched after the wait.
+            int pre = 0;
+            if (!p.b_batched && !b_mn && static_cast<int>(blockIdx.x) < total_tiles) {
+                const TileCoord c0 = decode_tile<BN>(p, blockIdx.x);
+                pre = min(STAGES, c0.kb_end - c0.kb_begin);
+                for (int s = 0; s < pre; ++s) {
+                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
+                    tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
+                }
+            }
+            pdl_wait();
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord c = decode_tile<BN>(p, t);
                 const int za = p.a_batched ? c.z1 : 0, za2 = p.a_batched ? c.z2 : 0;
                 const int bz1 = p.b_batched ? c.z1 : 0, bz2 = p.b_batched ? c.z2 : 0;
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
-                    mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+                    const bool prefetched = (t == static_cast<int>(blockIdx.x)) && (kb - c.kb_begin) < pre;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                    if (!prefetched) {
+                        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                    }
                     if (p.mode == 1) {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
@@ -290,7 +307,9 @@ __global__ void __launch_bounds__(192, 1)
                         else
                             tma_load_4d(sa, &mapA1, &full_bar[stage], (kb - p.cblocks0) * 64, c.m_tile * 128, za, za2);
                     }
-                    if (!b_mn) {
+                    if (prefetched) {
+                        // B tile of this stage is already in flight
+                    } else if (!b_mn) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
                     } else {
 #pragma unroll
@@ -308,6 +327,7 @@ __global__ void __launch_bounds__(192, 1)
         if (lane == 0) {
             // ------------------------------ MMA issuer ------------------------------
             const uint32_t idesc = umma_idesc_f16(128, BN, 0, b_mn ? 1 : 0);
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -355,6 +375,7 @@ __global__ void __launch_bounds__(192, 1)
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int et = threadIdx.x - 64;  // 0..127
+        pdl_wait();
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0 && p.splits == 1;
@@ -435,6 +456,7 @@ __global__ void __launch_bounds__(192, 1)
 
 // sums split-K partials and runs the epilogue; one thread per (row, 32-column chunk)
 __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const __grid_constant__ GemmParams p) {
+    pdl_enter();
     const int chunks = (p.N + 31) / 32;
     const long long total = static_cast<long long>(p.nz1) * p.nz2 * p.M * chunks;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -774,7 +796,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    gemm_tc_kernel<BN, STAGES><<<grid, 192, SMEM, stream>>>(op->mapA0, op->mapA1, op->mapB, p);
+    launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(192), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch: %s", cudaGetErrorString(e));
@@ -803,7 +825,7 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
         const int chunks = (p.N + 31) / 32;
         const long long total = static_cast<long long>(p.nz1) * p.nz2 * p.M * chunks;
         const int blocks = static_cast<int>((total + 255) / 256);
-        gemm_splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p);
+        launch_k(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, p);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "finalize launch: %s", cudaGetErrorString(e));

@@ -85,6 +85,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
                                 int groups, int chunks, float* __restrict__ partial, int* __restrict__ counters,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                 float* __restrict__ coef) {
+    pdl_enter();
     extern __shared__ float2 sm_acc[];  // [rows_per_iter][C]
     __shared__ int s_ticket;
     const int C = C0 + C1;
@@ -169,6 +170,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
 __global__ void __launch_bounds__(256)
     gn_apply_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW,
                     long long total_vec, const float* __restrict__ coef, int silu, __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total_vec) return;
     const int C = C0 + C1;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(256)
     gn_group_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                     __half* __restrict__ out) {
+    pdl_enter();
     __shared__ float red[2][8];
     __shared__ float s_mean, s_rstd;
     const int C = C0 + C1;
@@ -290,11 +293,11 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     if ((cpg % 2) == 0 && pairs <= 256 * 32) {
         dim3 grid(groups, Nimg);
         if (pairs <= 256 * 4)
-            gn_group_kernel<4><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+            launch_k(gn_group_kernel<4>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
         else if (pairs <= 256 * 12)
-            gn_group_kernel<12><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+            launch_k(gn_group_kernel<12>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
         else
-            gn_group_kernel<32><<<grid, 256, 0, st>>>(x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+            launch_k(gn_group_kernel<32>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
         return check_launch("gn_group");
     }
     const int chunks = gn_num_chunks(HW, C);
@@ -314,11 +317,11 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     float* coef = stats_ws + ((static_cast<size_t>(Nimg) * chunks * groups * 2 + 3) & ~size_t(3));
     size_t smem = static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
     if (smem < static_cast<size_t>(groups) * 8) smem = static_cast<size_t>(groups) * 8;
-    gn_stats_kernel<<<dim3(chunks, Nimg), threads, smem, st>>>(x0, C0, x1, C1, HW, groups, chunks, partial, counters,
+    launch_k(gn_stats_kernel, dim3(dim3(chunks, Nimg)), dim3(threads), smem, st, x0, C0, x1, C1, HW, groups, chunks, partial, counters,
                                                                gamma, beta, eps, coef);
     if (check_launch("gn_stats")) return -1;
     const long long total_vec = static_cast<long long>(Nimg) * HW * CV;
-    gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, st>>>(x0, C0, x1, C1, HW, total_vec, coef,
+    launch_k(gn_apply_kernel, dim3(static_cast<unsigned>((total_vec + 255) / 256)), dim3(256), 0, st, x0, C0, x1, C1, HW, total_vec, coef,
                                                                                    silu, out);
     return check_launch("gn_apply");
 }
@@ -329,6 +332,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __half* __restrict__ out) {
+    pdl_enter();
     constexpr int MAXV = 8;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -381,7 +385,7 @@ int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const
         return -1;
     }
     if (rows <= 0) return 0;
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, rows, C, gamma, beta, eps, out);
+    launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, C, gamma, beta, eps, out);
     return check_launch("layernorm");
 }
 
@@ -389,6 +393,7 @@ int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const
 // row softmax, in place
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long rows, int cols, int ld) {
+    pdl_enter();
     const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
 
 int launch_softmax_rows(__half* x, long long rows, int cols, int ld, cudaStream_t st) {
     if (rows <= 0) return 0;
-    softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x, rows, cols, ld);
+    launch_k(softmax_rows_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, st, x, rows, cols, ld);
     return check_launch("softmax_rows");
 }
 
@@ -447,6 +452,7 @@ __global__ void __launch_bounds__(128)
                       const __half* __restrict__ v, int ldv, __half* __restrict__ out, int ldo, int nq, int nkv, int d,
                       long long q_bs, long long kv_bs, long long o_bs, const int* __restrict__ kv_index, float scale,
                       int kpitch) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __half* Ks = reinterpret_cast<__half*>(sm_raw);  // [nkv][kpitch]
     __half* Vs = Ks + nkv * kpitch;                   // [nkv][d]
@@ -516,6 +522,7 @@ __global__ void __launch_bounds__(128)
     attn_tiny_kv_kernel(const __half* __restrict__ q, int ldq, const __half* __restrict__ k, int ldk,
                         const __half* __restrict__ v, int ldv, __half* __restrict__ out, int ldo, int nq, int nkv, int d,
                         long long q_bs, long long kv_bs, long long o_bs, const int* __restrict__ kv_index, float scale) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char sm_raw[];
     __half* Ks = reinterpret_cast<__half*>(sm_raw);  // [nkv][d]
     __half* Vs = Ks + nkv * d;                        // [nkv][d]
@@ -591,7 +598,7 @@ int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const 
         const size_t smem_t = static_cast<size_t>(nkv) * d * 2 * 2;
         if (smem_t <= 48 * 1024) {
             dim3 grid_t((nq + 127) / 128, heads, batch);
-            attn_tiny_kv_kernel<16><<<grid_t, 128, smem_t, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs,
+            launch_k(attn_tiny_kv_kernel<16>, dim3(grid_t), dim3(128), smem_t, st, q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs,
                                                                  kv_bs, o_bs, kv_index, scale);
             return check_launch("attn_tiny_kv");
         }
@@ -609,7 +616,7 @@ int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const 
         smem_set = smem;
     }
     dim3 grid((nq + ATTN_ROWS_PER_BLOCK - 1) / ATTN_ROWS_PER_BLOCK, heads, batch);
-    attn_small_kernel<<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs, kv_bs, o_bs, kv_index,
+    launch_k(attn_small_kernel, dim3(grid), dim3(128), smem, st, q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, d, q_bs, kv_bs, o_bs, kv_index,
                                               scale, kpitch);
     return check_launch("attn_small");
 }
@@ -619,6 +626,7 @@ int launch_attn_small(const __half* q, int ldq, const __half* k, int ldk, const 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     upsample2x_kernel(const __half* __restrict__ x, int H, int W, int CV, long long total, __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int cv = static_cast<int>(i % CV);
@@ -636,12 +644,13 @@ int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* ou
         return -1;
     }
     const long long total = static_cast<long long>(Nimg) * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, H, W, C / 8, total, out);
+    launch_k(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, H, W, C / 8, total, out);
     return check_launch("upsample2x");
 }
 
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const __half* __restrict__ x, int H, int W, int CV, int pad_lo,
                                                         int Ho, int Wo, long long total, __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int cv = static_cast<int>(i % CV);
@@ -665,13 +674,14 @@ int launch_im2col_s2(const __half* x, int Nimg, int H, int W, int C, int pad_lo,
         return -1;
     }
     const long long total = static_cast<long long>(Nimg) * Ho * Wo * 9 * (C / 8);
-    im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, H, W, C / 8, pad_lo, Ho, Wo, total,
+    launch_k(im2col_s2_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, H, W, C / 8, pad_lo, Ho, Wo, total,
                                                                                 out);
     return check_launch("im2col_s2");
 }
 
 __global__ void __launch_bounds__(256) patchify32_kernel(const float* __restrict__ x, long long total,
                                                          __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int kk = static_cast<int>(i % 3072);
@@ -684,7 +694,7 @@ __global__ void __launch_bounds__(256) patchify32_kernel(const float* __restrict
 }
 int launch_patchify32(const float* x, int Nimg, __half* out, cudaStream_t st) {
     const long long total = static_cast<long long>(Nimg) * 49 * 3072;
-    patchify32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, total, out);
+    launch_k(patchify32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, total, out);
     return check_launch("patchify32");
 }
 
@@ -695,6 +705,7 @@ __global__ void __launch_bounds__(256)
     guidance_ddim_kernel(const float* __restrict__ eps3, const float* __restrict__ lat, float* __restrict__ out,
                          long long n, float cfg, float tg, float sqrt_beta_t, float sqrt_alpha_t, float sqrt_alpha_prev,
                          float sqrt_beta_prev) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float eu = eps3[i], ec = eps3[n + i], et = eps3[2 * n + i];
@@ -710,7 +721,7 @@ int launch_guidance_ddim(const float* eps3, const float* latents_in, float* late
     const long long n = static_cast<long long>(B) * chw;
     const float beta_t = 1.0f - alpha_t;
     const float beta_prev = 1.0f - alpha_prev;  // (1 - a_prev - std_dev^2) with eta = 0
-    guidance_ddim_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+    launch_k(guidance_ddim_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 
         eps3, latents_in, latents_out, n, cfg, tg, sqrtf(beta_t), sqrtf(alpha_t), sqrtf(alpha_prev), sqrtf(beta_prev));
     return check_launch("guidance_ddim");
 }
@@ -721,6 +732,7 @@ int launch_guidance_ddim(const float* eps3, const float* latents_in, float* late
 __global__ void __launch_bounds__(256)
     pack_unet_input_kernel(const float* __restrict__ lat, const float* __restrict__ mask3,
                            const float* __restrict__ masked3, int B, int hw, __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (sample, pixel)
     if (i >= static_cast<long long>(3) * B * hw) return;
     const int s = static_cast<int>(i / hw), p = static_cast<int>(i % hw);
@@ -740,13 +752,14 @@ __global__ void __launch_bounds__(256)
 int launch_pack_unet_input(const float* latents, const float* mask3, const float* masked3, int B, int hw, __half* out,
                            cudaStream_t st) {
     const long long n = static_cast<long long>(3) * B * hw;
-    pack_unet_input_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(latents, mask3, masked3, B, hw, out);
+    launch_k(pack_unet_input_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, latents, mask3, masked3, B, hw, out);
     return check_launch("pack_unet_input");
 }
 
 __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, int C, int HW, int Cpad,
                                                                float divisor, long long total,
                                                                __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (n, pixel, cpad/8)
     if (i >= total) return;
     const int CV = Cpad >> 3;
@@ -765,13 +778,14 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __re
 int launch_nchw_to_nhwc_pad(const float* x, int Nimg, int C, int HW, int Cpad, float divisor, __half* out,
                             cudaStream_t st) {
     const long long total = static_cast<long long>(Nimg) * HW * (Cpad / 8);
-    nchw_to_nhwc_pad_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, C, HW, Cpad, divisor, total,
+    launch_k(nchw_to_nhwc_pad_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, C, HW, Cpad, divisor, total,
                                                                                        out);
     return check_launch("nchw_to_nhwc_pad");
 }
 
 __global__ void __launch_bounds__(256) vae_sample_kernel(const float* __restrict__ mom, const float* __restrict__ noise,
                                                          int hw, long long total, float scale, float* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, c<4, p)
     if (i >= total) return;
     const int p = static_cast<int>(i % hw);
@@ -790,12 +804,13 @@ __global__ void __launch_bounds__(256) vae_sample_kernel(const float* __restrict
 int launch_vae_sample(const float* moments, const float* noise, int B, int hw, float scale, float* out,
                       cudaStream_t st) {
     const long long total = static_cast<long long>(B) * 4 * hw;
-    vae_sample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(moments, noise, hw, total, scale, out);
+    launch_k(vae_sample_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, moments, noise, hw, total, scale, out);
     return check_launch("vae_sample");
 }
 
 __global__ void __launch_bounds__(256) mask_nearest_kernel(const float* __restrict__ in, int R, int f, long long total,
                                                            float* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int r = R / f;
@@ -807,7 +822,7 @@ __global__ void __launch_bounds__(256) mask_nearest_kernel(const float* __restri
 }
 int launch_mask_nearest(const float* in, int B, int R, int f, float* out, cudaStream_t st) {
     const long long total = static_cast<long long>(B) * (R / f) * (R / f);
-    mask_nearest_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in, R, f, total, out);
+    launch_k(mask_nearest_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, in, R, f, total, out);
     return check_launch("mask_nearest");
 }
 
@@ -817,6 +832,7 @@ int launch_mask_nearest(const float* in, int B, int R, int f, float* out, cudaSt
 // pass 1: row-wise running max of alpha over x in [x - pad/2, x + pad - pad/2 - 1]
 __global__ void __launch_bounds__(256) dilate_rows_kernel(const float* __restrict__ canvas, int R, int pad,
                                                           long long total, float* __restrict__ scratch) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
     if (i >= total) return;
     const int x = static_cast<int>(i % R);
@@ -834,6 +850,7 @@ __global__ void __launch_bounds__(256)
                          const float* __restrict__ scratch, int R, int pad, long long total,
                          float* __restrict__ masked_img, float* __restrict__ mask, float* __restrict__ ctx_img,
                          float* __restrict__ ctx_mask) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, y, x)
     if (i >= total) return;
     const int x = static_cast<int>(i % R);
@@ -864,9 +881,9 @@ int launch_canvas_preprocess(const float* canvas, const float* brush, int B, int
     if (pad < 1) pad = 1;
     const long long total = static_cast<long long>(B) * R * R;
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    dilate_rows_kernel<<<blocks, 256, 0, st>>>(canvas, R, pad, total, scratch);
+    launch_k(dilate_rows_kernel, dim3(blocks), dim3(256), 0, st, canvas, R, pad, total, scratch);
     if (check_launch("dilate_rows")) return -1;
-    canvas_finish_kernel<<<blocks, 256, 0, st>>>(canvas, brush, scratch, R, pad, total, masked_img, mask, ctx_img,
+    launch_k(canvas_finish_kernel, dim3(blocks), dim3(256), 0, st, canvas, brush, scratch, R, pad, total, masked_img, mask, ctx_img,
                                                 ctx_mask);
     return check_launch("canvas_finish");
 }
@@ -874,6 +891,7 @@ int launch_canvas_preprocess(const float* canvas, const float* brush, int B, int
 __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ canvas, const float* __restrict__ raw,
                                                         int R, long long total, float* __restrict__ out_f32,
                                                         unsigned char* __restrict__ out_u8) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (b, pix)
     if (i >= total) return;
     const long long plane = static_cast<long long>(R) * R;
@@ -891,7 +909,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
 int launch_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
                      cudaStream_t st) {
     const long long total = static_cast<long long>(B) * R * R;
-    composite_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(canvas, raw, R, total, out_f32,
+    launch_k(composite_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, canvas, raw, R, total, out_f32,
                                                                                 out_u8hwc);
     return check_launch("composite");
 }
@@ -901,6 +919,7 @@ int launch_composite(const float* canvas, const float* raw, int B, int R, float*
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_rows_bcast_kernel(__half* __restrict__ x, const float* __restrict__ add,
                                                              long long total, int C, int period) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = static_cast<int>(i % C);
@@ -909,41 +928,45 @@ __global__ void __launch_bounds__(256) add_rows_bcast_kernel(__half* __restrict_
 }
 int launch_add_rows_bcast(__half* x, const float* add, long long rows, int C, int period, cudaStream_t st) {
     const long long total = rows * C;
-    add_rows_bcast_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, add, total, C, period);
+    launch_k(add_rows_bcast_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, add, total, C, period);
     return check_launch("add_rows_bcast");
 }
 __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ out,
                                                          long long n) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __float2half_rn(x[i]);
 }
 int launch_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    f32_to_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, out, n);
+    launch_k(f32_to_f16_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, out, n);
     return check_launch("f32_to_f16");
 }
 __global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ x, float* __restrict__ out,
                                                          long long n) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __half2float(x[i]);
 }
 int launch_f16_to_f32(const __half* x, float* out, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    f16_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, out, n);
+    launch_k(f16_to_f32_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, x, out, n);
     return check_launch("f16_to_f32");
 }
 __global__ void __launch_bounds__(256) copy_f32_kernel(const float* __restrict__ s, float* __restrict__ d, long long n) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) d[i] = s[i];
 }
 int launch_copy_f32(const float* src, float* dst, long long n, cudaStream_t st) {
     if (n <= 0) return 0;
-    copy_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    launch_k(copy_f32_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, src, dst, n);
     return check_launch("copy_f32");
 }
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): emb = [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / (dim/2))
 __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int n, int dim, __half* __restrict__ out) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * dim) return;
     const int r = i / dim, c = i % dim;
@@ -954,7 +977,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ ts, int n, i
     out[i] = __float2half_rn(c < half_dim ? cosf(a) : sinf(a));
 }
 int launch_timestep_embedding(const float* timesteps, int n, int dim, __half* out, cudaStream_t st) {
-    timestep_embedding_kernel<<<(n * dim + 255) / 256, 256, 0, st>>>(timesteps, n, dim, out);
+    launch_k(timestep_embedding_kernel, dim3((n * dim + 255) / 256), dim3(256), 0, st, timesteps, n, dim, out);
     return check_launch("timestep_embedding");
 }
 
@@ -962,6 +985,7 @@ int launch_timestep_embedding(const float* timesteps, int n, int dim, __half* ou
 __global__ void __launch_bounds__(256) clip_embed_kernel(const __half* __restrict__ tok, const float* __restrict__ cls,
                                                          const float* __restrict__ pos, int C, long long total,
                                                          __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = static_cast<int>(i % C);
@@ -974,13 +998,14 @@ __global__ void __launch_bounds__(256) clip_embed_kernel(const __half* __restric
 int launch_clip_embed(const __half* patch_tok, const float* cls, const float* pos, int Nimg, int C, __half* out,
                       cudaStream_t st) {
     const long long total = static_cast<long long>(Nimg) * 50 * C;
-    clip_embed_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(patch_tok, cls, pos, C, total, out);
+    launch_k(clip_embed_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, patch_tok, cls, pos, C, total, out);
     return check_launch("clip_embed");
 }
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(const __half* __restrict__ x, int ld,
                                                           const int* __restrict__ idx, int C, long long total,
                                                           __half* __restrict__ out) {
+    pdl_enter();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = static_cast<int>(i % C);
@@ -989,7 +1014,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const __half* __restri
 }
 int launch_gather_rows(const __half* x, int ld, const int* rows_idx, int nrows, int C, __half* out, cudaStream_t st) {
     const long long total = static_cast<long long>(nrows) * C;
-    gather_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, ld, rows_idx, C, total, out);
+    launch_k(gather_rows_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, x, ld, rows_idx, C, total, out);
     return check_launch("gather_rows");
 }
 

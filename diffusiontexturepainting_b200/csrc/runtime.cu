@@ -329,7 +329,9 @@ struct Builder {
         if (!ok) return;
         Engine* eng = &e;
         const float scale = 1.0f / sqrtf(static_cast<float>(d));
-        if (nkv <= 64) {
+        const bool flash_ok = kv_index == nullptr && d <= 192 && (d % 8) == 0 && nq == nkv && nq >= 16 && ldq == ldk &&
+                              ldk == ldv && q_bs == kv_bs && e.opt_flash_;
+        if (nkv <= 64 && !flash_ok) {
             plan.add(K_ATTN_SMALL, [=](cudaStream_t st) -> int {
                 if (launch_attn_small(q, ldq, k, ldk, v, ldv, out, ldo, nq, nkv, heads, d, batch, q_bs, kv_bs, o_bs,
                                       kv_index, scale, st)) {
@@ -345,7 +347,7 @@ struct Builder {
             fail("indexed key/value batches are only supported for short sequences");
             return;
         }
-        if (d <= 192 && (d % 8) == 0 && nq == nkv && ldq == ldk && ldk == ldv && q_bs == kv_bs && e.opt_flash_) {
+        if (flash_ok) {
             // tcgen05 flash attention: scores stay in TMEM
             FlashOp fop;
             if (flash_attn_setup(&fop, q, k, v, ldq, q_bs, out, ldo, o_bs, nq, heads, d, batch)) {
