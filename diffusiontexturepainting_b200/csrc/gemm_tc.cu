@@ -47,8 +47,8 @@ __device__ __forceinline__ void store_half_chunk(__half* out, const float (&v)[3
 }
 
 // bias_chunk: 32 floats for columns col0.. (shared memory in the main kernel, global in the finalize kernel), or nullptr
-__device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long out_off, int row, int col0,
-                                                 float (&v)[32], const float* bias_chunk) {
+__device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long out_off, long long res_off, int row,
+                                                 int col0, float (&v)[32], const float* bias_chunk) {
     const int N = p.N;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
@@ -57,7 +57,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     // residual loads first: their latency overlaps the arithmetic below
     const bool has_res = p.residual != nullptr;
     uint4 rraw[4];
-    const __half* rp = has_res ? p.residual + static_cast<long long>(row) * p.ldr + col0 : nullptr;
+    const __half* rp = has_res ? p.residual + res_off + static_cast<long long>(row) * p.ldr + col0 : nullptr;
     const bool res_vec = has_res && ncols == 32 && (p.ldr & 7) == 0;
     if (res_vec) {
 #pragma unroll
@@ -73,6 +73,27 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] *= alpha;
+    }
+    if (flags & EPI_SOFTMAX16) {
+        // folded cross-attention: each 16-column group holds the scores of one head against the (<= 16) image tokens
+        const int nv = p.aux;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (i < nv) m = fmaxf(m, v[16 * g + i]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float e = (i < nv) ? __expf(v[16 * g + i] - m) : 0.0f;
+                v[16 * g + i] = e;
+                sum += e;
+            }
+            const float inv = __fdividef(1.0f, sum);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[16 * g + i] *= inv;
+        }
     }
     if (flags & EPI_GEGLU) {
         // columns [0,16) hold a_j, [16,32) hold the gates g_j of the same 16 outputs
@@ -395,6 +416,7 @@ __global__ void __launch_bounds__(192, 1)
                 if (m < p.M) row = m;
             }
             const long long out_off = static_cast<long long>(c.z1) * p.out_zs1 + static_cast<long long>(c.z2) * p.out_zs2;
+            const long long res_off = static_cast<long long>(c.z1) * p.res_zs1 + static_cast<long long>(c.z2) * p.res_zs2;
             if (col_bias) {
                 epi_bar_sync();  // previous tile's readers are done with sbias
                 for (int i = et; i < BN; i += 128) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
@@ -437,7 +459,7 @@ __global__ void __launch_bounds__(192, 1)
                                 if (i < ncols) ws[i] = v[i];
                         }
                     } else {
-                        epilogue_store32(p, out_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
+                        epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
                     }
                 }
             }
@@ -496,7 +518,8 @@ __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const __grid_
     }
     const int z1 = zb % p.nz1, z2 = zb / p.nz1;
     const long long out_off = static_cast<long long>(z1) * p.out_zs1 + static_cast<long long>(z2) * p.out_zs2;
-    epilogue_store32(p, out_off, row, col0, v, col_bias ? b : nullptr);
+    const long long res_off = static_cast<long long>(z1) * p.res_zs1 + static_cast<long long>(z2) * p.res_zs2;
+    epilogue_store32(p, out_off, res_off, row, col0, v, col_bias ? b : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------

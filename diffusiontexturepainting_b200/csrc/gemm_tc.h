@@ -31,6 +31,7 @@ enum GemmFlags : int {
     EPI_IMG01 = 1 << 6,         // out = clamp(x / 2 + 0.5, 0, 1)   (inpaint_pipeline.py:148)
     EPI_OUT_F32 = 1 << 7,       // fp32 row-major output
     GEMM_B_MN = 1 << 8,         // B operand is MN-major in global memory: B[K, N] row-major (V of attention)
+    EPI_SOFTMAX16 = 1 << 9,     // row softmax over the first `aux` columns of every 16-column group (folded cross-attention)
 };
 
 struct GemmParams {
@@ -48,6 +49,8 @@ struct GemmParams {
     int a_batched;     // A map uses (z1,z2) as coords 2,3
     int b_batched;     // B map uses (z1,z2) as coords 2,3
     long long out_zs1, out_zs2;  // output offset (elements) per z1 / z2
+    long long res_zs1, res_zs2;  // residual offset (elements) per z1 / z2
+    int aux;           // EPI_SOFTMAX16: valid columns per group
     int flags;         // GemmFlags
     int hw_out;        // EPI_OUT_F32_NCHW: pixels per image
     int ldc;           // output row stride (elements)

@@ -236,6 +236,52 @@ struct Builder {
         push_gemm(op);
     }
 
+    struct Bmm {
+        const __half* A = nullptr;
+        int lda = 0;
+        long long a_zs1 = 0, a_zs2 = 0;
+        const __half* B = nullptr;
+        int ldb = 0;
+        long long b_zs1 = 0, b_zs2 = 0;
+        int b_mn = 0;
+        int M = 0, N = 0, K = 0, nz1 = 1, nz2 = 1;
+        void* out = nullptr;
+        int ldc = 0;
+        long long out_zs1 = 0, out_zs2 = 0;
+        const float* bias = nullptr;
+        const __half* res = nullptr;
+        int ldr = 0;
+        long long res_zs1 = 0, res_zs2 = 0;
+        int flags = 0;
+        float alpha = 1.0f;
+        int aux = 0;
+        const char* label = "bmm";
+    };
+    void bmm(const Bmm& a) {
+        if (!ok) return;
+        GemmOp op;
+        int BN, sp;
+        gemm_pick_config(((a.M + 127) / 128) * a.nz1 * a.nz2, a.N, (a.K + 63) / 64, a.b_mn ? GEMM_B_MN : 0, &BN, &sp);
+        if (gemm_setup_batched(&op, a.A, a.lda, a.a_zs1, a.a_zs2, a.B, a.ldb, a.b_zs1, a.b_zs2, a.b_mn, a.M, a.N, a.K, a.nz1,
+                               a.nz2, BN)) {
+            fail(std::string("batched contraction setup: ") + gemm_last_error());
+            return;
+        }
+        op.p.out = a.out;
+        op.p.ldc = a.ldc;
+        op.p.out_zs1 = a.out_zs1;
+        op.p.out_zs2 = a.out_zs2;
+        op.p.bias = a.bias;
+        op.p.residual = a.res;
+        op.p.ldr = a.ldr;
+        op.p.res_zs1 = a.res_zs1;
+        op.p.res_zs2 = a.res_zs2;
+        op.p.flags |= a.flags;
+        op.p.alpha = a.alpha;
+        op.p.aux = a.aux;
+        push_gemm(op, a.label);
+    }
+
     // 3x3 stride-1 pad-1 conv over one or two NHWC sources; w_name: [Cout, 9*(C0+C1)] f16
     void conv3x3_into(const Act& a0, const Act& a1, const std::string& w_name, const float* bias, const __half* res,
                       int ldr, void* out, int ldc, int flags, int hw_out) {
@@ -659,6 +705,16 @@ int Engine::finalize_weights() {
         cross_kv_[i] = static_cast<__half*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * kvw->shape[0] * 2, true));
         if (!cross_kv_[i]) return -1;
     }
+    wscore_.assign(tf_names_.size(), nullptr);
+    wout_.assign(tf_names_.size(), nullptr);
+    for (size_t i = 0; i < tf_names_.size(); ++i) {
+        const WT* qw = find("unet." + tf_names_[i] + ".transformer_blocks.0.attn2.to_q.weight");
+        if (!qw) return fail("finalize_weights: missing unet." + tf_names_[i] + ".transformer_blocks.0.attn2.to_q.weight");
+        const size_t C = static_cast<size_t>(qw->shape[0]), HP = static_cast<size_t>(cfg_.unet_heads) * 16;
+        wscore_[i] = static_cast<__half*>(persistent(3 * HP * C * 2, true));
+        wout_[i] = static_cast<__half*>(persistent(3 * C * HP * 2, true));
+        if (!wscore_[i] || !wout_[i]) return -1;
+    }
     ctx_ = static_cast<__half*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * cfg_.unet_cross_dim * 2, true));
     ctx_f32_ = static_cast<float*>(persistent(static_cast<size_t>(2 * cfg_.enc_tokens) * cfg_.unet_cross_dim * 4, true));
     if (!ctx_ || !ctx_f32_) return -1;
@@ -719,31 +775,63 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.linear(l);
     }
     b.release(att);
-    // cross-attention on the (pre-projected) image tokens
+    // cross-attention on the image tokens. K / V are constant per brush, so the query projection is folded into the keys
+    // (scores = LN2(h) (scale K_h Wq_h)^T) and the output projection into the values (out = P (V_h Wo_h^T)), both
+    // prepared by the condition plan: two skinny contractions, softmax over the 14 tokens in the first one's epilogue.
+    // Sample groups [uncond | cond | texture-guidance] pick their context through the batch coordinate.
     tmp = b.like(x, C);
     b.layernorm(h, t + ".norm2", tmp.p);
-    Act q = b.like(x, C);
-    {
-        Lin l;
-        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = b.W16(t + ".attn2.to_q.weight"); l.ldw = C; l.N = C; l.out = q.p;
-        b.linear(l);
-    }
-    b.release(tmp);
-    att = b.like(x, C);
     const int T = cfg.enc_tokens;
-    if (b.ok)
-        b.attention(q.p, C, kv, 2 * C, kv + C, 2 * C, att.p, C, seq, T, heads, d, batch, static_cast<long long>(seq) * C,
-                    static_cast<long long>(T) * 2 * C, static_cast<long long>(seq) * C, kv_index);
-    b.release(q);
-    {
-        Lin l;
-        l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = b.W16(t + ".attn2.to_out.0.weight"); l.ldw = C; l.N = C;
-        l.bias = b.F32(t + ".attn2.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
-        b.linear(l);
+    if (e.fold_cross()) {
+        const int HP = heads * 16;
+        const int tf = e.tf_index(p);
+        const long long grp_rows = rows / 3;
+        Act P = b.like(x, HP);
+        if (b.ok) {
+            Builder::Bmm g;
+            g.A = tmp.p; g.lda = C; g.a_zs1 = grp_rows * C;
+            g.B = e.wscore(tf); g.ldb = C; g.b_zs1 = static_cast<long long>(HP) * C;
+            g.M = static_cast<int>(grp_rows); g.N = HP; g.K = C; g.nz1 = 3;
+            g.out = P.p; g.ldc = HP; g.out_zs1 = grp_rows * HP;
+            g.flags = EPI_SOFTMAX16; g.aux = T; g.label = "cross_scores";
+            b.bmm(g);
+        }
+        b.release(tmp);
+        if (b.ok) {
+            Builder::Bmm g;
+            g.A = P.p; g.lda = HP; g.a_zs1 = grp_rows * HP;
+            g.B = e.wout(tf); g.ldb = HP; g.b_zs1 = static_cast<long long>(C) * HP;
+            g.M = static_cast<int>(grp_rows); g.N = C; g.K = HP; g.nz1 = 3;
+            g.out = h.p; g.ldc = C; g.out_zs1 = grp_rows * C;
+            g.bias = b.F32(t + ".attn2.to_out.0.bias");
+            g.res = h.p; g.ldr = C; g.res_zs1 = grp_rows * C; g.label = "cross_out";
+            b.bmm(g);
+        }
+        b.release(P);
+    } else {
+        Act q = b.like(x, C);
+        {
+            Lin l;
+            l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+            l.W = b.W16(t + ".attn2.to_q.weight"); l.ldw = C; l.N = C; l.out = q.p;
+            b.linear(l);
+        }
+        b.release(tmp);
+        att = b.like(x, C);
+        if (b.ok)
+            b.attention(q.p, C, kv, 2 * C, kv + C, 2 * C, att.p, C, seq, T, heads, d, batch,
+                        static_cast<long long>(seq) * C, static_cast<long long>(T) * 2 * C,
+                        static_cast<long long>(seq) * C, kv_index);
+        b.release(q);
+        {
+            Lin l;
+            l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
+            l.W = b.W16(t + ".attn2.to_out.0.weight"); l.ldw = C; l.N = C;
+            l.bias = b.F32(t + ".attn2.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+            b.linear(l);
+        }
+        b.release(att);
     }
-    b.release(att);
     // GEGLU feed-forward
     tmp = b.like(x, C);
     b.layernorm(h, t + ".norm3", tmp.p);
@@ -1283,6 +1371,40 @@ int Engine::build_cond_plan() {
         if (b.ok && c != D) b.fail("attn2.to_kv weight has unexpected K");
         b.linear(l);
     }
+    // folded cross-attention operands per layer and context slot (0 = uncond, 1 = 2 = cond)
+    const int heads = cfg_.unet_heads, HP = heads * 16;
+    for (size_t i = 0; i < tf_names_.size() && b.ok; ++i) {
+        const std::string t = tf_names_[i] + ".transformer_blocks.0";
+        int C = 0, kq = 0;
+        const __half* Wq = b.W16(t + ".attn2.to_q.weight", &C, &kq);
+        const __half* Wo = b.W16(t + ".attn2.to_out.0.weight");
+        if (!b.ok) break;
+        const int d = C / heads;
+        const float scale = 1.0f / sqrtf(static_cast<float>(d));
+        for (int slot = 0; slot < 3 && b.ok; ++slot) {
+            const int c = slot == 0 ? 0 : 1;
+            const __half* Kc = cross_kv_[i] + static_cast<size_t>(c) * T * 2 * C;
+            const __half* Vc = Kc + C;
+            {   // Wscore[slot][h*16 + j][:] = scale * K_c,h[j,:] Wq_h      (B = Wq_h consumed MN-major)
+                Builder::Bmm g;
+                g.A = Kc; g.lda = 2 * C; g.a_zs1 = d;
+                g.B = Wq; g.ldb = C; g.b_zs1 = static_cast<long long>(d) * C; g.b_mn = 1;
+                g.M = T; g.N = C; g.K = d; g.nz1 = heads;
+                g.out = wscore_[i] + static_cast<size_t>(slot) * HP * C; g.ldc = C; g.out_zs1 = 16LL * C;
+                g.alpha = scale; g.label = "fold_scores";
+                b.bmm(g);
+            }
+            {   // Wout[slot][:, h*16 + j] = Wo[:, h*d:(h+1)*d] V_c,h[j,:]^T
+                Builder::Bmm g;
+                g.A = Wo; g.lda = C; g.a_zs1 = d;
+                g.B = Vc; g.ldb = 2 * C; g.b_zs1 = d;
+                g.M = C; g.N = T; g.K = d; g.nz1 = heads;
+                g.out = wout_[i] + static_cast<size_t>(slot) * C * HP; g.ldc = HP; g.out_zs1 = 16;
+                g.label = "fold_out";
+                b.bmm(g);
+            }
+        }
+    }
     if (!b.ok) {
         cond_plan_.clear();
         return -1;
@@ -1688,6 +1810,13 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "graph") {
         opt_graph_ = value;
+        return 0;
+    }
+    if (n == "fold_cross") {
+        opt_fold_cross_ = value;
+        unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
         return 0;
     }
     if (n == "flash") {

@@ -129,6 +129,14 @@ class Engine {
     int set_option(const char* name, int value);
     int profile_dump(const char* path);
     const char* last_error() const { return err_.c_str(); }
+    bool fold_cross() const { return opt_fold_cross_ != 0; }
+    int tf_index(const std::string& prefix) const {
+        for (size_t i = 0; i < tf_names_.size(); ++i)
+            if (tf_names_[i] == prefix) return static_cast<int>(i);
+        return 0;
+    }
+    const __half* wscore(int i) const { return wscore_[i]; }
+    const __half* wout(int i) const { return wout_[i]; }
 
    private:
     friend struct Builder;
@@ -183,6 +191,9 @@ class Engine {
     __half* ctx_ = nullptr;  // (2*14, cross) f16: rows 0..13 uncond, 14..27 cond
     float* ctx_f32_ = nullptr;
     std::vector<__half*> cross_kv_;  // per transformer layer: (28, 2C)
+    std::vector<__half*> wscore_;    // per layer: (3, heads*16, C)  scale * K_h Wq_h, zero rows for the pad tokens
+    std::vector<__half*> wout_;      // per layer: (3, C, heads*16)  Wo_h V_h^T
+    int opt_fold_cross_ = 1;
     std::vector<std::string> tf_names_;  // transformer prefixes in execution order
     bool cond_set_ = false;
 
