@@ -201,7 +201,7 @@ __device__ __forceinline__ long long gtime() {
         if (p.dbg != nullptr) p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = gtime(); \
     } while (0)
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct TileCoord {
     int m_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
@@ -235,7 +235,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
 // Persistent kernel: grid = min(tiles, SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
 // Two TMEM accumulators (BN columns each) let the epilogue of tile i overlap the mainloop of tile i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
     constexpr int A_BYTES = 128 * 128;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(192, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -393,9 +393,11 @@ __global__ void __launch_bounds__(192, 1)
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------
+        // eight epilogue warps: two per TMEM lane quarter (warp-id % 4), taking alternate 32-column chunks of the tile
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        const int et = threadIdx.x - 64;  // 0..127
+        const int et = threadIdx.x - 64;  // 0..255
+        const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
         pdl_wait();
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -419,20 +421,28 @@ __global__ void __launch_bounds__(192, 1)
             const long long res_off = static_cast<long long>(c.z1) * p.res_zs1 + static_cast<long long>(c.z2) * p.res_zs2;
             if (col_bias) {
                 epi_bar_sync();  // previous tile's readers are done with sbias
-                for (int i = et; i < BN; i += 128) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
+                for (int i = et; i < BN; i += 256) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
                 epi_bar_sync();
             }
             mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (t == static_cast<int>(blockIdx.x) && et == 0) DBG_MARK(4);
             const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            // chunks this warp owns: cc = 32*half, 32*half + 64, ... (bounded by the tile width and by N)
+            int n_mine = 0;
+            for (int cc = 32 * half; cc < BN && c.n0 + cc < p.N; cc += 64) ++n_mine;
+            if (n_mine == 0) {
+                // nothing to read for this warp in this tile: still hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
 #pragma unroll 1
-            for (int cc = 0; cc < BN; cc += 32) {
-                if (c.n0 + cc >= p.N) break;
+            for (int cc = 32 * half, it = 0; it < n_mine; cc += 64, ++it) {
                 uint32_t raw[32];
                 tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc), raw);
                 tmem_ld_wait();
-                if (cc + 32 >= BN || c.n0 + cc + 32 >= p.N) {
+                if (it == n_mine - 1) {
                     // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
@@ -819,7 +829,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(192), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
+    launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch: %s", cudaGetErrorString(e));

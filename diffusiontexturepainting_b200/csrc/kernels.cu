@@ -290,14 +290,12 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     }
     const int cpg = C / groups;
     const long long pairs = static_cast<long long>(HW) * (cpg / 2);
-    if ((cpg % 2) == 0 && pairs <= 256 * 32) {
+    if ((cpg % 2) == 0 && pairs <= 256 * 12) {
         dim3 grid(groups, Nimg);
         if (pairs <= 256 * 4)
             launch_k(gn_group_kernel<4>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
-        else if (pairs <= 256 * 12)
-            launch_k(gn_group_kernel<12>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
         else
-            launch_k(gn_group_kernel<32>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+            launch_k(gn_group_kernel<12>, dim3(grid), dim3(256), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
         return check_launch("gn_group");
     }
     const int chunks = gn_num_chunks(HW, C);
