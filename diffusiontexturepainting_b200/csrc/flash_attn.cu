@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_tc.h"
@@ -303,6 +304,316 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-warpgroup variant (256 queries per CTA) for head dims <= 128: K / V tiles are fetched once for two query tiles, and
+// while one warpgroup runs its softmax the tensor pipe works on the other one's S = Q K^T / O += P V, so the MUFU-bound
+// softmax and the MMAs overlap inside one CTA (TMEM: S0 | S1 | O0 | O1 = 512 columns).
+// Warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: softmax of query tile 0, warps 6-9: softmax of query tile 1.
+// ------------------------------------------------------------------------------------------------------------
+template <int DCH, int KS>
+__global__ void __launch_bounds__(320, 1)
+    flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FlashParams p) {
+    constexpr int TILE_BYTES = DCH * 16384;
+    constexpr int P_BYTES = 2 * 16384;
+    constexpr uint32_t O_COL0 = 256, O_STRIDE = DCH * 64;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                       // [2][TILE]
+    uint8_t* sK = sQ + 2 * TILE_BYTES;        // [KS][TILE]
+    uint8_t* sV = sK + KS * TILE_BYTES;       // [KS][TILE]
+    uint8_t* sP = sV + KS * TILE_BYTES;       // [2][P]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KS;
+    uint64_t* v_full = k_empty + KS;
+    uint64_t* v_empty = v_full + KS;
+    uint64_t* s_full = v_empty + KS;   // [2]
+    uint64_t* s_empty = s_full + 2;    // [2]
+    uint64_t* p_full = s_empty + 2;    // [2]
+    uint64_t* o_done = p_full + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.seq_kv + 127) / 128;
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapQ);
+        tma_prefetch_desc(&mapK);
+        tma_prefetch_desc(&mapV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KS; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(&s_full[w], 1);
+            mbar_init(&s_empty[w], 4);
+            mbar_init(&p_full[w], 4);
+            mbar_init(&o_done[w], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sQ + w * TILE_BYTES + c * 16384, &mapQ, q_full, c * 64, q0 + w * 128, head, b);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk; ++j) {
+                fa_wait(&k_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sK + st * TILE_BYTES + c * 16384, &mapK, &k_full[st], c * 64, j * 128, head, b);
+                fa_wait(&v_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sV + st * TILE_BYTES + c * 16384, &mapV, &v_full[st], c * 64, j * 128, head, b);
+                if (++st == KS) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+            const uint32_t idesc_o = umma_idesc_f16(128, p.dN, 0, 1);
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            auto issue_s = [&](int w, uint32_t k_addr) {
+                for (int kk = 0; kk < p.ksteps_qk; ++kk) {
+                    const uint32_t off = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base + w * 128, umma_desc_k_sw128(q_addr + w * TILE_BYTES + off),
+                             umma_desc_k_sw128(k_addr + off), idesc_s, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(&s_full[w]);
+            };
+            auto issue_pv = [&](int w, uint32_t v_addr, int j) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t poff = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base + O_COL0 + w * O_STRIDE, umma_desc_k_sw128(p_addr + w * P_BYTES + poff),
+                             umma_desc_mn_sw128(v_addr + static_cast<uint32_t>(kk) * 2048u, 16384), idesc_o,
+                             (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&o_done[w]);
+            };
+            fa_wait(q_full, 0);
+            int kst = 0;
+            uint32_t kph = 0;  // K ring position of block j + 1 (the one whose scores are issued inside iteration j)
+            int vst = 0;
+            uint32_t vph = 0;
+            // prologue: scores of block 0 for both query tiles
+            fa_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0, smem_u32(sK));
+            issue_s(1, smem_u32(sK));
+            umma_commit(&k_empty[0]);
+            if (++kst == KS) {
+                kst = 0;
+                kph ^= 1;
+            }
+            for (int j = 0; j < nblk; ++j) {
+                const bool more = j + 1 < nblk;
+                fa_wait(&v_full[vst], vph);
+                const uint32_t v_addr = smem_u32(sV + vst * TILE_BYTES);
+                uint32_t k_addr = 0;
+                // query tile 0: O0 += P0_j V_j, then its next scores as soon as K_{j+1} has landed
+                fa_wait(&p_full[0], j & 1);
+                tc_fence_after();
+                issue_pv(0, v_addr, j);
+                if (more) {
+                    fa_wait(&k_full[kst], kph);
+                    tc_fence_after();
+                    k_addr = smem_u32(sK + kst * TILE_BYTES);
+                    issue_s(0, k_addr);  // s_empty[0] of block j was signalled before p_full[0]
+                }
+                // query tile 1
+                fa_wait(&p_full[1], j & 1);
+                tc_fence_after();
+                issue_pv(1, v_addr, j);
+                umma_commit(&v_empty[vst]);
+                if (++vst == KS) {
+                    vst = 0;
+                    vph ^= 1;
+                }
+                if (more) {
+                    issue_s(1, k_addr);
+                    umma_commit(&k_empty[kst]);
+                    if (++kst == KS) {
+                        kst = 0;
+                        kph ^= 1;
+                    }
+                }
+            }
+        }
+    } else {
+        const int w = (warp - 2) >> 2;  // query tile / warpgroup
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t s_col = tmem_base + t_lane + w * 128;
+        const uint32_t o_col = tmem_base + t_lane + O_COL0 + w * O_STRIDE;
+        float m_used = -INFINITY, l = 0.0f;
+        uint8_t* prow = sP + w * P_BYTES + r * 128;
+        const int sw = r & 7;
+        const float sc = p.scale_log2;
+        for (int j = 0; j < nblk; ++j) {
+            fa_wait(&s_full[w], j & 1);
+            tc_fence_after();
+            const int kv_valid = min(128, p.seq_kv - j * 128);
+            float bm = -INFINITY;
+            {
+                uint32_t a[32], bb[32];
+                tmem_ld_32x32(s_col + 0, a);
+                tmem_ld_32x32(s_col + 32, bb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
+                    if (32 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(bb[i]));
+                }
+                tmem_ld_32x32(s_col + 64, a);
+                tmem_ld_32x32(s_col + 96, bb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (64 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
+                    if (96 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(bb[i]));
+                }
+            }
+            bm *= sc;
+            if (j > 0) fa_wait(&o_done[w], (j - 1) & 1);
+            tc_fence_after();
+            bool need = false;
+            float factor = 1.0f;
+            if (j == 0) {
+                m_used = bm;
+            } else if (bm > m_used + 8.0f) {
+                need = true;
+                factor = ex2_approx(m_used - bm);
+                m_used = bm;
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                l *= factor;
+                for (int c = 0; c < p.dN; c += 32) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(o_col + c, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st_32x32(o_col + c, o);
+                }
+                tmem_st_wait();
+            }
+            const float neg_m = -m_used;
+            float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll 1
+            for (int hc = 0; hc < 128; hc += 64) {
+                uint32_t raw[64];
+                tmem_ld_32x32(s_col + hc, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+                tmem_ld_32x32(s_col + hc + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+                tmem_ld_wait();
+                if (hc == 64) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[w]);
+                }
+                uint8_t* sub = prow + (hc >> 6) * 16384;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    float e[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
+                        if (hc + c + i >= kv_valid) e[i] = 0.0f;
+                    }
+                    l0 += (e[0] + e[1]) + (e[2] + e[3]);
+                    l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                    __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
+                    __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
+                    uint4 u;
+                    u.x = *reinterpret_cast<uint32_t*>(&h0);
+                    u.y = *reinterpret_cast<uint32_t*>(&h1);
+                    u.z = *reinterpret_cast<uint32_t*>(&h2);
+                    u.w = *reinterpret_cast<uint32_t*>(&h3);
+                    *reinterpret_cast<uint4*>(sub + (((c >> 3) ^ sw) << 4)) = u;
+                }
+            }
+            l += l0 + l1;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[w]);
+        }
+        fa_wait(&o_done[w], (nblk - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const int row = q0 + w * 128 + r;
+        __half* orow = p.out + b * p.o_bs + static_cast<long long>(row) * p.ldo + head * p.d;
+        for (int c = 0; c < p.dN; c += 32) {
+            uint32_t raw[32];
+            tmem_ld_32x32(o_col + c, raw);
+            tmem_ld_wait();
+            if (row < p.seq_q) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (c + i + 8 <= p.d) {
+                        __half2 h0 = __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+                        __half2 h1 = __floats2half2_rn(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
+                        __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv);
+                        __half2 h3 = __floats2half2_rn(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&h0);
+                        u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2);
+                        u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(orow + c + i) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DCH, int KS>
+static int launch_flash2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashParams& p,
+                         cudaStream_t st) {
+    constexpr int SMEM = DCH * 16384 * (2 + 2 * KS) + 4 * 16384 + (9 + 4 * KS) * 8 + 16 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(flash_attn2_kernel<DCH, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+            cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    dim3 grid((p.seq_q + 255) / 256, p.heads, p.batch);
+    return launch_k(flash_attn2_kernel<DCH, KS>, grid, dim3(320), SMEM, st, mq, mk, mv, p) == cudaSuccess ? 0 : -1;
+}
+
 template <int DCH, int KV_STAGES>
 static int launch_flash(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashParams& p,
                         cudaStream_t st) {
@@ -361,7 +672,15 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
     p.ldo = op->ldo;
     p.o_bs = op->o_bs;
     int r;
-    if (op->d <= 64)
+    static const bool two_wg = []() {
+        const char* e = getenv("DTP_FLASH2");
+        return !(e && e[0] == '0');
+    }();
+    if (two_wg && op->seq >= 256 && op->d <= 64)
+        r = launch_flash2<1, 2>(op->mq, op->mk, op->mv, p, st);
+    else if (two_wg && op->seq >= 256 && op->d <= 128)
+        r = launch_flash2<2, 1>(op->mq, op->mk, op->mv, p, st);
+    else if (op->d <= 64)
         r = launch_flash<1, 1>(op->mq, op->mk, op->mv, p, st);
     else if (op->d <= 128)
         r = launch_flash<2, 2>(op->mq, op->mk, op->mv, p, st);
