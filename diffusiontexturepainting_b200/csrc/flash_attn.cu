@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(192, DCH == 1 ? 2 : 1)
 // Warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: softmax of query tile 0, warps 6-9: softmax of query tile 1.
 // ------------------------------------------------------------------------------------------------------------
 template <int DCH, int KS>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
     flash_attn2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                        const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FlashParams p) {
     constexpr int TILE_BYTES = DCH * 16384;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(320, 1)
     const int nblk = (p.seq_kv + 127) / 128;
 
     pdl_launch_dependents();
-    if (warp == 0 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&mapQ);
         tma_prefetch_desc(&mapK);
         tma_prefetch_desc(&mapV);
@@ -360,14 +360,18 @@ __global__ void __launch_bounds__(320, 1)
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
 
-    if (warp == 0) {
+    // warps 0-3 / 4-7: softmax warpgroups of query tile 0 / 1 (224 registers each: the 128 scores of a row stay in
+    // registers); warps 8-11: control warpgroup (8 = TMA producer, 9 = MMA issuer) shrunk to 40 registers
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 8) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
 #pragma unroll
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(320, 1)
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             const uint32_t idesc_o = umma_idesc_f16(128, p.dN, 0, 1);
@@ -466,8 +470,10 @@ __global__ void __launch_bounds__(320, 1)
                 }
             }
         }
+      }
     } else {
-        const int w = (warp - 2) >> 2;  // query tile / warpgroup
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int w = warp >> 2;  // query tile / warpgroup
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
@@ -481,24 +487,31 @@ __global__ void __launch_bounds__(320, 1)
             fa_wait(&s_full[w], j & 1);
             tc_fence_after();
             const int kv_valid = min(128, p.seq_kv - j * 128);
+            // TMEM -> register bandwidth (~64 B/clk/SM) is the scarce resource of this loop: read the 128 scores of the
+            // row exactly once, keep them in registers for both the maximum and the exponentials, release S at once.
+            uint32_t raw[128];
+#pragma unroll
+            for (int c = 0; c < 128; c += 32) tmem_ld_32x32(s_col + c, *reinterpret_cast<uint32_t(*)[32]>(&raw[c]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[w]);
             float bm = -INFINITY;
-            {
-                uint32_t a[32], bb[32];
-                tmem_ld_32x32(s_col + 0, a);
-                tmem_ld_32x32(s_col + 32, bb);
-                tmem_ld_wait();
+            if (kv_valid == 128) {
+                float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
-                    if (32 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(bb[i]));
+                for (int i = 0; i < 128; i += 4) {
+                    b0 = fmaxf(b0, __uint_as_float(raw[i]));
+                    b1 = fmaxf(b1, __uint_as_float(raw[i + 1]));
+                    b2 = fmaxf(b2, __uint_as_float(raw[i + 2]));
+                    b3 = fmaxf(b3, __uint_as_float(raw[i + 3]));
                 }
-                tmem_ld_32x32(s_col + 64, a);
-                tmem_ld_32x32(s_col + 96, bb);
-                tmem_ld_wait();
+                bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (64 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(a[i]));
-                    if (96 + i < kv_valid) bm = fmaxf(bm, __uint_as_float(bb[i]));
+                for (int i = 0; i < 128; ++i) {
+                    if (i >= kv_valid) raw[i] = 0xff800000u;  // -inf: exp2 -> 0
+                    bm = fmaxf(bm, __uint_as_float(raw[i]));
                 }
             }
             bm *= sc;
@@ -527,37 +540,21 @@ __global__ void __launch_bounds__(320, 1)
             }
             const float neg_m = -m_used;
             float l0 = 0.0f, l1 = 0.0f;
-#pragma unroll 1
-            for (int hc = 0; hc < 128; hc += 64) {
-                uint32_t raw[64];
-                tmem_ld_32x32(s_col + hc, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-                tmem_ld_32x32(s_col + hc + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-                tmem_ld_wait();
-                if (hc == 64) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_empty[w]);
-                }
-                uint8_t* sub = prow + (hc >> 6) * 16384;
 #pragma unroll
-                for (int c = 0; c < 64; c += 8) {
-                    float e[8];
+            for (int c = 0; c < 128; c += 8) {
+                float e[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
-                        if (hc + c + i >= kv_valid) e[i] = 0.0f;
-                    }
-                    l0 += (e[0] + e[1]) + (e[2] + e[3]);
-                    l1 += (e[4] + e[5]) + (e[6] + e[7]);
-                    __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
-                    __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
-                    uint4 u;
-                    u.x = *reinterpret_cast<uint32_t*>(&h0);
-                    u.y = *reinterpret_cast<uint32_t*>(&h1);
-                    u.z = *reinterpret_cast<uint32_t*>(&h2);
-                    u.w = *reinterpret_cast<uint32_t*>(&h3);
-                    *reinterpret_cast<uint4*>(sub + (((c >> 3) ^ sw) << 4)) = u;
-                }
+                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
+                l0 += (e[0] + e[1]) + (e[2] + e[3]);
+                l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
+                __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2);
+                u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(prow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = u;
             }
             l += l0 + l1;
             tc_fence_before();
@@ -595,7 +592,7 @@ __global__ void __launch_bounds__(320, 1)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 template <int DCH, int KS>
@@ -611,7 +608,7 @@ static int launch_flash2(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
         attr_set = true;
     }
     dim3 grid((p.seq_q + 255) / 256, p.heads, p.batch);
-    return launch_k(flash_attn2_kernel<DCH, KS>, grid, dim3(320), SMEM, st, mq, mk, mv, p) == cudaSuccess ? 0 : -1;
+    return launch_k(flash_attn2_kernel<DCH, KS>, grid, dim3(384), SMEM, st, mq, mk, mv, p) == cudaSuccess ? 0 : -1;
 }
 
 template <int DCH, int KV_STAGES>

@@ -748,7 +748,7 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
     // Cost model (SM cycles) of the persistent kernel, searched over (BN, split-K):
     //   per k-block the tensor pipe needs 2*BN cycles (128 x BN x 64 MACs at 4096 MAC/clk/SM) and the TMA feed
     //   (16 KB of A + 128*BN B of B) moves ~64 B/clk per SM (measured); chip-wide the L2 -> SM fabric sustains
-    //   ~3700 B/clk (measured ~7 TB/s), which bounds kernels whose tiles re-read A / B many times;
+    //   ~7000 B/clk (measured ~14 TB/s on an 8192^3 problem), which bounds kernels whose tiles re-read A / B many times;
     //   the epilogue of a tile (~350 clk per 32 columns) overlaps the next tile's mainloop;
     //   split-K adds an fp32 partial write + a finalize pass (launch ~2000 clk + bytes at ~2500 B/clk).
     const int kSMs = 148;
@@ -765,7 +765,7 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
         if (bn >= 64 && bn - 32 >= ((N + 31) / 32) * 32) continue;  // mostly padding
         const long long gn = (N + bn - 1) / bn;
         const double t_mma = 2.0 * bn;
-        const double t_tma = (16384.0 + 128.0 * bn) / 64.0;
+        const double t_tma = (16384.0 + 128.0 * bn) / 58.0;
         const double t_kb = t_mma > t_tma ? t_mma : t_tma;
         const double t_epi = 300.0 + (bn / 32) * 350.0;
         const int max_sp = (flags & GEMM_B_MN) ? 1 : 16;
@@ -779,7 +779,7 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
             const double per_cta = static_cast<double>((tiles + kSMs - 1) / kSMs);
             double cost = per_cta * t_tile + t_epi_eff + 1500.0;
             const double l2_bytes = static_cast<double>(mtiles) * gn * num_kb * (16384.0 + 128.0 * bn);
-            const double t_l2 = l2_bytes / 3700.0;
+            const double t_l2 = l2_bytes / 7000.0;
             if (t_l2 > cost) cost = t_l2;
             if (sp > 1) cost += 2000.0 + rows * N * 4.0 * (sp + 1) / 2500.0;
             if (best_cost < 0 || cost < best_cost * 0.97 || (cost <= best_cost && bn > best && sp <= best_sp)) {

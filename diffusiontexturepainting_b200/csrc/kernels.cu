@@ -110,13 +110,30 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     float s[8], ss[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.0f;
-    for (int p = p0 + prow; p < p1; p += rows_per_iter) {
+    int p = p0 + prow;
+    // four independent 16-byte loads in flight per thread
+    for (; p + 3 * rows_per_iter < p1; p += 4 * rows_per_iter) {
+        Half8 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = ld8(src + static_cast<long long>(p + u * rows_per_iter) * ldc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(h[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += f[e];
+                ss[e] = fmaf(f[e], f[e], ss[e]);
+            }
+        }
+    }
+    for (; p < p1; p += rows_per_iter) {
         float f[8];
         unpack8(ld8(src + static_cast<long long>(p) * ldc), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s[e] += f[e];
-            ss[e] += f[e] * f[e];
+            ss[e] = fmaf(f[e], f[e], ss[e]);
         }
     }
 #pragma unroll
@@ -327,20 +344,20 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass variance
 // ------------------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict__ x, int rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, __half* __restrict__ out) {
     pdl_enter();
-    constexpr int MAXV = 8;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int CV = C >> 3;
     const __half* src = x + static_cast<long long>(row) * C;
-    float f[MAXV][8];
+    float f[NV][8];
     float s = 0.0f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
         const int v = lane + j * 32;
         if (v < CV) {
             unpack8(ld8(src + v * 8), f[j]);
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     const float mean = warp_sum(s) / static_cast<float>(C);
     float ss = 0.0f;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
         const int v = lane + j * 32;
         if (v < CV) {
 #pragma unroll
@@ -364,13 +381,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __half* __restrict
     const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(C) + eps);
     __half* dst = out + static_cast<long long>(row) * C;
 #pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
+    for (int j = 0; j < NV; ++j) {
         const int v = lane + j * 32;
         if (v < CV) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float y[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                y[e] = (f[j][e] - mean) * rstd * __ldg(gamma + v * 8 + e) + __ldg(beta + v * 8 + e);
+            for (int e = 0; e < 8; ++e) y[e] = fmaf((f[j][e] - mean) * rstd, gg[e], bb[e]);
             st8(dst + v * 8, pack8(y));
         }
     }
@@ -383,7 +405,18 @@ int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const
         return -1;
     }
     if (rows <= 0) return 0;
-    launch_k(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, x, rows, C, gamma, beta, eps, out);
+    const int nv = (C / 8 + 31) / 32;
+    const dim3 grid((rows + 7) / 8), block(256);
+    if (nv <= 1)
+        launch_k(layernorm_kernel<1>, grid, block, 0, st, x, rows, C, gamma, beta, eps, out);
+    else if (nv <= 2)
+        launch_k(layernorm_kernel<2>, grid, block, 0, st, x, rows, C, gamma, beta, eps, out);
+    else if (nv <= 3)
+        launch_k(layernorm_kernel<3>, grid, block, 0, st, x, rows, C, gamma, beta, eps, out);
+    else if (nv <= 5)
+        launch_k(layernorm_kernel<5>, grid, block, 0, st, x, rows, C, gamma, beta, eps, out);
+    else
+        launch_k(layernorm_kernel<8>, grid, block, 0, st, x, rows, C, gamma, beta, eps, out);
     return check_launch("layernorm");
 }
 
