@@ -65,9 +65,10 @@ int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, in
                   int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
                   int hw_out, int BN, int splits, void* stream) {
     GemmOp op;
+    const int w_blocked = (flags & GEMM_W_BLOCKED) ? 1 : 0;
     if (BN <= 0) gemm_pick_config((M + 127) / 128, N, (K0 + 63) / 64 + (A1 ? (K1 + 63) / 64 : 0), flags, &BN, &splits);
     int r = gemm_setup_linear(&op, (const __half*)A0, lda0, K0, (const __half*)A1, lda1, K1, M, (const __half*)Wt, ldw,
-                              N, BN, splits);
+                              N, BN, splits, w_blocked);
     return finish(op, r, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
 }
 

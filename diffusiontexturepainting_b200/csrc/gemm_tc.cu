@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(320, 1)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const bool b_mn = (p.flags & GEMM_B_MN) != 0;
+    const bool w_blocked = (p.flags & GEMM_W_BLOCKED) != 0;
     const int total_tiles = p.total_tiles;
 
     pdl_launch_dependents();  // the next kernel of the stream may start its prologue now
@@ -297,7 +298,10 @@ __global__ void __launch_bounds__(320, 1)
                 pre = min(STAGES, c0.kb_end - c0.kb_begin);
                 for (int s = 0; s < pre; ++s) {
                     mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
-                    tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
+                    if (w_blocked)
+                        tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
+                    else
+                        tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
                 }
             }
             pdl_wait();
@@ -330,6 +334,8 @@ __global__ void __launch_bounds__(320, 1)
                     }
                     if (prefetched) {
                         // B tile of this stage is already in flight
+                    } else if (w_blocked) {
+                        tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
                     } else {
@@ -606,8 +612,16 @@ static int map_rows(CUtensorMap* m, const __half* base, uint64_t K, uint64_t row
     return make_map_4d(m, base, dims, st, box);
 }
 
+// weights in [N/64][K/64][64][64] tiles: dims (k_in, n_in, k_blk, n_blk)
+static int map_blocked(CUtensorMap* m, const __half* base, uint64_t K, uint64_t N, uint32_t BN) {
+    uint64_t dims[4] = {64, 64, K / 64, (N + 63) / 64};
+    uint64_t st[3] = {128, 8192, 8192 * (K / 64)};
+    uint32_t box[4] = {64, 64, 1, BN / 64};
+    return make_map_4d(m, base, dims, st, box);
+}
+
 int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
-                      const __half* Wt, int ldw, int N, int BN, int splits) {
+                      const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked) {
     params_defaults(op->p);
     GemmParams& p = op->p;
     BN = fix_bn(BN);
@@ -634,6 +648,15 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
     } else {
         op->mapA1 = op->mapA0;
     }
+    if (w_blocked) {
+        const int K = K0 + (A1 ? K1 : 0);
+        if ((K % 64) != 0 || (N % 64) != 0 || (BN % 64) != 0) {
+            snprintf(g_gemm_err, sizeof(g_gemm_err), "blocked weights need K, N, BN %% 64 == 0 (K=%d N=%d BN=%d)", K, N, BN);
+            return -12;
+        }
+        p.flags |= GEMM_W_BLOCKED;
+        return map_blocked(&op->mapB, Wt, K, N, BN);
+    }
     return map_rows(&op->mapB, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN);
 }
 
@@ -645,7 +668,7 @@ static int largest_divisor_le(int n, int cap) {
 }
 
 int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, int C1, int Nimg, int H, int W,
-                       const __half* Wt, int Cout, int BN, int splits) {
+                       const __half* Wt, int Cout, int BN, int splits, int w_blocked) {
     params_defaults(op->p);
     GemmParams& p = op->p;
     BN = fix_bn(BN);
@@ -690,6 +713,14 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
         if (r) return r;
     } else {
         op->mapA1 = op->mapA0;
+    }
+    if (w_blocked) {
+        if ((Cout % 64) != 0 || (BN % 64) != 0) {
+            snprintf(g_gemm_err, sizeof(g_gemm_err), "blocked conv weights need Cout, BN %% 64 == 0 (Cout=%d BN=%d)", Cout, BN);
+            return -12;
+        }
+        p.flags |= GEMM_W_BLOCKED;
+        return map_blocked(&op->mapB, Wt, (uint64_t)9 * C, Cout, BN);
     }
     return map_rows(&op->mapB, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
 }
@@ -754,7 +785,7 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
     const int kSMs = 148;
     static const int cand_k[] = {32, 64, 128, 160, 192, 256};
     static const int cand_mn[] = {64, 128, 192, 256};
-    const bool mn = (flags & GEMM_B_MN) != 0;
+    const bool mn = (flags & (GEMM_B_MN | GEMM_W_BLOCKED)) != 0;
     const int* cand = mn ? cand_mn : cand_k;
     const int ncand = mn ? 4 : 6;
     double best_cost = -1.0;

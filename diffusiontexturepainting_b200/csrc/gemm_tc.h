@@ -31,6 +31,7 @@ enum GemmFlags : int {
     EPI_IMG01 = 1 << 6,         // out = clamp(x / 2 + 0.5, 0, 1)   (inpaint_pipeline.py:148)
     EPI_OUT_F32 = 1 << 7,       // fp32 row-major output
     GEMM_B_MN = 1 << 8,         // B operand is MN-major in global memory: B[K, N] row-major (V of attention)
+    GEMM_W_BLOCKED = 1 << 10,   // weights stored as [N/64][K/64][64][64] tiles (8 KB contiguous per 64x64 block: DRAM-burst friendly)
     EPI_SOFTMAX16 = 1 << 9,     // row softmax over the first `aux` columns of every 16-column group (folded cross-attention)
 };
 
@@ -78,11 +79,11 @@ int make_map_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const 
 // Linear problem: A0 [M, K0] (row stride lda0) and optional A1 [M, K1] (K0 % 64 == 0 when A1 is used);
 // Wt [N, K0+K1] row-major (row stride ldw). Strides in elements, multiples of 8.
 int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
-                      const __half* Wt, int ldw, int N, int BN, int splits);
+                      const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked = 0);
 // 3x3/s1/p1 conv over NHWC activations: sources (Nimg,H,W,C0) and optional (Nimg,H,W,C1), C0,C1 % 64 == 0;
 // Wt [Cout, 9*(C0+C1)] with k = (ky*3+kx)*(C0+C1) + c.
 int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, int C1, int Nimg, int H, int W,
-                       const __half* Wt, int Cout, int BN, int splits);
+                       const __half* Wt, int Cout, int BN, int splits, int w_blocked = 0);
 // Batched product over (z1 in [0,nz1), z2 in [0,nz2)):  D_z[M,N] = A_z[M,K] * B_z^T
 //   A_z = A + z1*a_zs1 + z2*a_zs2 (row stride lda);  K-major B_z[N,K] = B + z1*b_zs1 + z2*b_zs2 (row stride ldb),
 //   or with b_mn: B_z[K,N] row-major (row stride ldb).  All strides in elements, multiples of 8.
