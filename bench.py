@@ -140,7 +140,7 @@ def run_reference(args):
             "config": bench_config(args, 1),
             "cpu_baseline": {"value": value, "unit": "stamps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "stamps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def bench_config(args, world):
@@ -319,13 +319,32 @@ def run_ours(args):
             "kernel_launches_per_stamp": {k: v[1] for k, v in prof.items()},
             "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything that libraries print to fd 1 (e.g. the NCCL version banner) goes to stderr; the single JSON line is
+    written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
