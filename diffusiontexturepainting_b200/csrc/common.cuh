@@ -72,14 +72,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
         : "memory");
 }
 
-// L2 prefetch of a tensor tile (no shared memory, no barrier): warms L2 ahead of the demand load
-__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
-                     reinterpret_cast<uint64_t>(m)),
-                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA issue, commit, TMEM loads
 // ----------------------------------------------------------------------------------------------

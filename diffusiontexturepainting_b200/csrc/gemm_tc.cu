@@ -183,73 +183,6 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     store_half_chunk(out, v, ncols, (p.ldc & 7) == 0 && (out_off & 7) == 0);
 }
 
-// Math of the fp16 row-major epilogue without the store: alpha, bias, softmax16 / activation / GEGLU, residual (already
-// transposed into registers). Returns the number of output columns produced for the chunk (16 for GEGLU, else 32).
-__device__ __forceinline__ int epilogue_compute32(const GemmParams& p, int row, float (&v)[32], const float* bias_chunk,
-                                                  const uint4* rres) {
-    const int flags = p.flags;
-    const float alpha = p.alpha;
-    if (flags & EPI_BIAS_M) {
-        const float rb = (p.bias && row >= 0) ? __ldg(p.bias + row) : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, rb);
-    } else if (bias_chunk != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, bias_chunk[i]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= alpha;
-    }
-    if (flags & EPI_SOFTMAX16) {
-        const int nv = p.aux;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (i < nv) m = fmaxf(m, v[16 * g + i]);
-            float sum = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float e = (i < nv) ? __expf(v[16 * g + i] - m) : 0.0f;
-                v[16 * g + i] = e;
-                sum += e;
-            }
-            const float inv = __fdividef(1.0f, sum);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[16 * g + i] *= inv;
-        }
-    }
-    if (flags & EPI_GEGLU) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] * gelu_erf_f(v[16 + i]);
-        return 16;
-    }
-    if (flags & EPI_GELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
-    } else if (flags & EPI_QUICKGELU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = quick_gelu_fast(v[i]);
-    } else if (flags & EPI_SILU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
-    }
-    if (rres != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rres[i]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(h2[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-            }
-        }
-    }
-    return 32;
-}
-
 // bounded mbarrier wait: a descriptor / byte-count bug must trap, not hang the GPU
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -320,7 +253,6 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
-    uint8_t* staging = reinterpret_cast<uint8_t*>(sbias + BN);  // [8 epilogue warps][2 KB] transposition buffers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -379,13 +311,6 @@ __global__ void __launch_bounds__(320, 1)
                 const int za = p.a_batched ? c.z1 : 0, za2 = p.a_batched ? c.z2 : 0;
                 const int bz1 = p.b_batched ? c.z1 : 0, bz2 = p.b_batched ? c.z2 : 0;
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
-                    if (p.l2_prefetch > 0 && !p.b_batched && !b_mn && kb + p.l2_prefetch < c.kb_end) {
-                        // weight tiles are demanded in a fixed order: pull them into L2 well ahead of the TMA load
-                        if (w_blocked)
-                            tma_prefetch_l2_4d(&mapB, 0, 0, kb + p.l2_prefetch, c.n0 >> 6);
-                        else
-                            tma_prefetch_l2_4d(&mapB, (kb + p.l2_prefetch) * 64, c.n0, 0, 0);
-                    }
                     const bool prefetched = (t == static_cast<int>(blockIdx.x)) && (kb - c.kb_begin) < pre;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
@@ -510,9 +435,6 @@ __global__ void __launch_bounds__(320, 1)
             tc_fence_after();
             if (t == static_cast<int>(blockIdx.x) && et == 0) DBG_MARK(4);
             const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-            const bool staged_tile = p.splits == 1 && (p.flags & (EPI_OUT_F32 | EPI_OUT_F32_NCHW | EPI_IMG01)) == 0 &&
-                                     (p.ldc & 7) == 0 && (out_off & 7) == 0 &&
-                                     (p.residual == nullptr || ((p.ldr & 7) == 0 && (res_off & 7) == 0));
             // chunks this warp owns: cc = 32*half, 32*half + 64, ... (bounded by the tile width and by N)
             int n_mine = 0;
             for (int cc = 32 * half; cc < BN && c.n0 + cc < p.N; cc += 64) ++n_mine;
@@ -525,15 +447,20 @@ __global__ void __launch_bounds__(320, 1)
 #pragma unroll 1
             for (int cc = 32 * half, it = 0; it < n_mine; cc += 64, ++it) {
                 uint32_t raw[32];
-                tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc), raw);
-                tmem_ld_wait();
+                if (p.dbg_mode & 2) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) raw[i] = 0;
+                } else {
+                    tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc), raw);
+                    tmem_ld_wait();
+                }
                 if (it == n_mine - 1) {
                     // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                if (row >= 0) {
+                if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
@@ -553,87 +480,9 @@ __global__ void __launch_bounds__(320, 1)
                             for (int i = 0; i < 32; ++i)
                                 if (i < ncols) ws[i] = v[i];
                         }
-                    } else if (!staged_tile || p.N - (c.n0 + cc) < 32) {
+                    } else {
                         epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
                     }
-                }
-                if (staged_tile && p.N - (c.n0 + cc) >= 32) {
-                    // ---- coalesced path: transpose through a per-warp 2 KB buffer so that every global access of the
-                    // warp covers whole 64-byte (or 32-byte, GEGLU) row segments instead of 32 scattered 16-byte pieces
-                    const int col0 = c.n0 + cc;
-                    uint8_t* stg = staging + (warp - 2) * 2048;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    uint4 rres[4];
-                    const bool has_res = p.residual != nullptr;
-                    if (has_res) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rr = 8 * i + (lane >> 2), j = lane & 3;
-                            const int grow = __shfl_sync(0xffffffffu, row, rr);
-                            uint4 t = make_uint4(0, 0, 0, 0);
-                            if (grow >= 0)
-                                t = __ldg(reinterpret_cast<const uint4*>(p.residual + res_off +
-                                                                         static_cast<long long>(grow) * p.ldr + col0) + j);
-                            *reinterpret_cast<uint4*>(stg + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4)) = t;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            rres[j] = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
-                        __syncwarp();
-                    }
-                    const int nout = epilogue_compute32(p, row, v, col_bias ? sbias + cc : nullptr, has_res ? rres : nullptr);
-                    __half* obase = reinterpret_cast<__half*>(p.out) + out_off;
-                    if (nout == 32) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __half2 a = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
-                            __half2 b2 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __half2 c2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                            __half2 d2 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t*>(&a);
-                            u.y = *reinterpret_cast<uint32_t*>(&b2);
-                            u.z = *reinterpret_cast<uint32_t*>(&c2);
-                            u.w = *reinterpret_cast<uint32_t*>(&d2);
-                            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int rr = 8 * i + (lane >> 2), j = lane & 3;
-                            const int grow = __shfl_sync(0xffffffffu, row, rr);
-                            const uint4 t = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4));
-                            if (grow >= 0)
-                                *reinterpret_cast<uint4*>(obase + static_cast<long long>(grow) * p.ldc + col0 + j * 8) = t;
-                        }
-                    } else {  // GEGLU: 16 outputs (32 bytes) per row at column col0 / 2
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            __half2 a = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
-                            __half2 b2 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                            __half2 c2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                            __half2 d2 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t*>(&a);
-                            u.y = *reinterpret_cast<uint32_t*>(&b2);
-                            u.z = *reinterpret_cast<uint32_t*>(&c2);
-                            u.w = *reinterpret_cast<uint32_t*>(&d2);
-                            *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) = u;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const int rr = 16 * i + (lane >> 1), j = lane & 1;
-                            const int grow = __shfl_sync(0xffffffffu, row, rr);
-                            const uint4 t = *reinterpret_cast<const uint4*>(stg + rr * 32 + ((j ^ ((rr >> 2) & 1)) << 4));
-                            if (grow >= 0)
-                                *reinterpret_cast<uint4*>(obase + static_cast<long long>(grow) * p.ldc + (col0 >> 1) + j * 8) = t;
-                        }
-                    }
-                    __syncwarp();
                 }
             }
             if (++acc == 2) {
@@ -995,7 +844,7 @@ static int num_sms() {
 template <int BN, int STAGES>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
-    constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 8 * 2048 + 1024;
+    constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
@@ -1008,11 +857,11 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         attr_set = true;
     }
     GemmParams p = op->p;
-    static const int l2pf = []() {
-        const char* e = getenv("DTP_L2PF");
+    static const int dbgmode = []() {
+        const char* e = getenv("DTP_EPI_DEBUG");
         return e ? atoi(e) : 0;
     }();
-    p.l2_prefetch = l2pf;
+    p.dbg_mode = dbgmode;
     p.grid_m = op->grid_m;
     p.grid_n = (p.N + BN - 1) / BN;
     const long long tiles = static_cast<long long>(p.grid_m) * p.grid_n * p.nz1 * p.nz2 * p.splits;

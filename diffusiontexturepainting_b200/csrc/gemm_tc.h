@@ -63,7 +63,7 @@ struct GemmParams {
     float* workspace;         // [batch*splits, Mpad, N] fp32
     long long* dbg;           // optional: per-CTA globaltimer checkpoints [ctas][8] (tuning aid), nullable
     int grid_m, grid_n, total_tiles;  // filled at launch: tile grid of the persistent scheduler
-    int l2_prefetch;   // > 0: L2-prefetch weight tiles this many k-blocks ahead of the demand load
+    int dbg_mode;      // tuning aid (DTP_EPI_DEBUG): 1 = skip global stores, 2 = skip TMEM loads
 };
 
 struct GemmOp {
