@@ -193,3 +193,70 @@ def test_full_encoder(full):
 
 def test_full_e2e(full):
     check_e2e(full, 128, 5, name="sd15", psnr_min=30.0)
+
+
+def test_graph_replay_and_options_are_equivalent(tiny):
+    """CUDA-graph replay, eager launch order, unfolded cross-attention and the materialised-score attention path must all
+    produce the same stamp (bit-identical for graph vs eager; <= 2e-3 rel-L2 across algorithmic variants)."""
+    from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
+    R, steps, B = 128, 4, 2
+    model = TRTConditionalInpainter(R, device=0, model_config=tiny.cfg, state_dicts=tiny.sds, max_batch_size=B)
+    model.pipeline.sample_posterior = False
+    model.set_brush(smooth_image(1, 3, R))
+    canvas = make_canvas(B, R)
+    lat = torch.randn(B, 4, R // 8, R // 8, generator=gen(42))
+    settings = dict(steps=steps, context_pad=30, tg_steps=2, width=R, cfg_weight=2.5, tg_weight=0.7)
+    eng = model.engine
+    outs = {}
+    eng.set_option("graph", 0)
+    outs["eager"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("graph", 1)
+    for i in range(3):  # warm (eager), capture, replay
+        outs[f"graph{i}"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    assert eng.counter("graph_launches") >= 2
+    for i in range(3):
+        assert torch.equal(outs["eager"], outs[f"graph{i}"])
+    eng.set_option("fold_cross", 0)
+    outs["unfolded"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("fold_cross", 1)
+    eng.set_option("flash", 0)
+    outs["noflash"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("flash", 1)
+    for k in ("unfolded", "noflash"):
+        e = rel_l2(outs[k], outs["eager"])
+        log(f"tiny.variant.{k}", rel_l2=e)
+        assert e < 2e-3
+    # u8 fast path == float path composited and truncated (handler.py:55-56)
+    u8 = model.stamp_u8((canvas.permute(0, 2, 3, 1) * 255).to(torch.uint8), init_latents=lat, **settings)
+    canvas_q = (canvas.permute(0, 2, 3, 1) * 255).to(torch.uint8).permute(0, 3, 1, 2).float() / 255
+    ref = model.generate(canvas_q, init_latents=lat, **settings)
+    ref_u8 = (ref * 255).to(torch.uint8).permute(0, 2, 3, 1)
+    diff = (u8.int() - ref_u8.int()).abs().max().item()
+    log("tiny.stamp_u8.max_lsb_diff", diff=diff)
+    assert diff <= 1
+    model.pipeline.teardown()
+
+
+def test_reference_step_semantics_and_strict_schedule(tiny):
+    """steps = S runs S - 1 evaluations (t_start = 1 quirk, stable_diffusion_pipeline.py:348-355); strict runs S; tg is
+    forced to zero from evaluation index tg_steps on (stable_diffusion_pipeline.py:419-420). Checked against the oracle."""
+    from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
+    R = 64
+    model = TRTConditionalInpainter(R, device=0, model_config=tiny.cfg, state_dicts=tiny.sds)
+    model.pipeline.sample_posterior = False
+    brush = smooth_image(1, 3, R)
+    model.set_brush(brush)
+    ora = tiny.oracle(R)
+    ora.set_brush(brush)
+    canvas = make_canvas(1, R)
+    lat = torch.randn(1, 4, R // 8, R // 8, generator=gen(3))
+    for strict in (False, True):
+        for steps, tg_steps in ((3, 1), (1, 1), (5, 0)):
+            model.pipeline.strict_schedule = strict
+            s = dict(steps=steps, context_pad=10, tg_steps=tg_steps, width=R, cfg_weight=2.0, tg_weight=1.5)
+            got = model.generate_raw(canvas, init_latents=lat, **s).cpu()
+            ref = ora.generate_raw(canvas, lat.to(DEV), strict=strict, **s).cpu()
+            e = rel_l2(got, ref)
+            log(f"tiny.schedule.strict{int(strict)}.S{steps}.tg{tg_steps}", rel_l2=e)
+            assert e < 5e-3
+    model.pipeline.teardown()
