@@ -66,7 +66,9 @@ int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, in
                   int hw_out, int BN, int splits, void* stream) {
     GemmOp op;
     const int w_blocked = (flags & GEMM_W_BLOCKED) ? 1 : 0;
-    if (BN <= 0) gemm_pick_config((M + 127) / 128, N, (K0 + 63) / 64 + (A1 ? (K1 + 63) / 64 : 0), flags, &BN, &splits);
+    if (BN <= 0)
+        gemm_pick_config((M + 127) / 128, N, (K0 + 63) / 64 + (A1 ? (K1 + 63) / 64 : 0),
+                         flags | ((M > 128 && !w_blocked && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
     int r = gemm_setup_linear(&op, (const __half*)A0, lda0, K0, (const __half*)A1, lda1, K1, M, (const __half*)Wt, ldw,
                               N, BN, splits, w_blocked);
     return finish(op, r, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
@@ -82,7 +84,8 @@ int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int
         int r0 = gemm_setup_conv3x3(&probe, (const __half*)A0, C0, (const __half*)A1, C1, Nimg, H, W,
                                     (const __half*)Wt, Cout, 128, 1);
         if (r0) return finish(probe, r0, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
-        gemm_pick_config(probe.grid_m, Cout, probe.p.num_kb, flags, &BN, &splits);
+        gemm_pick_config(probe.grid_m, Cout, probe.p.num_kb,
+                         flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
     }
     int r = gemm_setup_conv3x3(&op, (const __half*)A0, C0, (const __half*)A1, C1, Nimg, H, W, (const __half*)Wt, Cout,
                                BN, splits);

@@ -207,11 +207,13 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;"
 struct TileCoord {
     int m_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
 };
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+// CL = 2: `t` indexes a PAIR of adjacent m-tiles handled by the two CTAs of a cluster (same n-tile, same k-range)
+template <int BN, int CL>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int rank) {
     TileCoord c;
-    c.m_tile = t % p.grid_m;
-    int r = t / p.grid_m;
+    const int gm = (CL == 2) ? (p.grid_m + 1) / 2 : p.grid_m;
+    c.m_tile = (CL == 2) ? 2 * (t % gm) + rank : t % gm;
+    int r = t / gm;
     const int n_tile = r % p.grid_n;
     r /= p.grid_n;
     c.zsplit = r % p.splits;
@@ -235,7 +237,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
 
 // Persistent kernel: grid = min(tiles, SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
 // Two TMEM accumulators (BN columns each) let the epilogue of tile i overlap the mainloop of tile i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(320, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
@@ -258,7 +260,10 @@ __global__ void __launch_bounds__(320, 1)
     const int lane = threadIdx.x & 31;
     const bool b_mn = (p.flags & GEMM_B_MN) != 0;
     const bool w_blocked = (p.flags & GEMM_W_BLOCKED) != 0;
-    const int total_tiles = p.total_tiles;
+    const int total_tiles = p.total_tiles;  // CL == 2: number of m-tile pairs
+    const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int tile0 = (CL == 2) ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int tstep = (CL == 2) ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     pdl_launch_dependents();  // the next kernel of the stream may start its prologue now
     if (threadIdx.x == 0) DBG_MARK(0);
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(320, 1)
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);  // CL == 2: both CTAs of the cluster must have consumed the shared B stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(320, 1)
     if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // the peer's barriers must exist before anything is multicast into it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) DBG_MARK(1);
@@ -294,24 +300,29 @@ __global__ void __launch_bounds__(320, 1)
             // STAGES tiles are requested BEFORE waiting for the predecessor kernel, hiding the DRAM latency of
             // weight-streaming layers behind the previous kernel's tail. Activations (A) are only touched after the wait.
             int pre = 0;
-            if (!p.b_batched && !b_mn && static_cast<int>(blockIdx.x) < total_tiles) {
-                const TileCoord c0 = decode_tile<BN>(p, blockIdx.x);
+            constexpr int BH = BN / CL;  // rows of the B tile this CTA fetches (CL == 2: its half, multicast to both)
+            if (!p.b_batched && !b_mn && tile0 < total_tiles) {
+                const TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
                 pre = min(STAGES, c0.kb_end - c0.kb_begin);
                 for (int s = 0; s < pre; ++s) {
                     mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
-                    if (w_blocked)
-                        tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
+                    uint8_t* sbp = smem + s * STAGE_BYTES + A_BYTES;
+                    if (CL == 2)
+                        tma_load_4d_mc(sbp + rank * BH * 128, &mapB, &full_bar[s], (c0.kb_begin + s) * 64,
+                                       c0.n0 + rank * BH, 0, 0, 3);
+                    else if (w_blocked)
+                        tma_load_4d(sbp, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
                     else
-                        tma_load_4d(smem + s * STAGE_BYTES + A_BYTES, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
+                        tma_load_4d(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
                 }
             }
             pdl_wait();
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile<BN>(p, t);
+            for (int t = tile0; t < total_tiles; t += tstep) {
+                const TileCoord c = decode_tile<BN, CL>(p, t, rank);
                 const int za = p.a_batched ? c.z1 : 0, za2 = p.a_batched ? c.z2 : 0;
                 const int bz1 = p.b_batched ? c.z1 : 0, bz2 = p.b_batched ? c.z2 : 0;
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
-                    const bool prefetched = (t == static_cast<int>(blockIdx.x)) && (kb - c.kb_begin) < pre;
+                    const bool prefetched = (t == tile0) && (kb - c.kb_begin) < pre;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     if (!prefetched) {
@@ -335,6 +346,8 @@ __global__ void __launch_bounds__(320, 1)
                     }
                     if (prefetched) {
                         // B tile of this stage is already in flight
+                    } else if (CL == 2) {
+                        tma_load_4d_mc(sb + rank * BH * 128, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0, 3);
                     } else if (w_blocked) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
@@ -361,8 +374,8 @@ __global__ void __launch_bounds__(320, 1)
             int acc = 0;
             uint32_t acc_phase = 0;
             bool first = true;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile<BN>(p, t);
+            for (int t = tile0; t < total_tiles; t += tstep) {
+                const TileCoord c = decode_tile<BN, CL>(p, t, rank);
                 mbar_wait_bounded(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -384,7 +397,10 @@ __global__ void __launch_bounds__(320, 1)
                         const uint64_t bd = bdesc + static_cast<uint64_t>(b_mn ? k * 128 : k * 2);
                         umma_f16(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (CL == 2)
+                        umma_commit_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the cluster
+                    else
+                        umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -409,8 +425,8 @@ __global__ void __launch_bounds__(320, 1)
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0 && p.splits == 1;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const TileCoord c = decode_tile<BN>(p, t);
+        for (int t = tile0; t < total_tiles; t += tstep) {
+            const TileCoord c = decode_tile<BN, CL>(p, t, rank);
             int row = -1;
             if (p.mode == 1) {
                 if (r < p.rows_valid) {
@@ -433,7 +449,7 @@ __global__ void __launch_bounds__(320, 1)
             }
             mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            if (t == static_cast<int>(blockIdx.x) && et == 0) DBG_MARK(4);
+            if (t == tile0 && et == 0) DBG_MARK(4);
             const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
             // chunks this warp owns: cc = 32*half, 32*half + 64, ... (bounded by the tile width and by N)
             int n_mine = 0;
@@ -494,6 +510,7 @@ __global__ void __launch_bounds__(320, 1)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
     if (threadIdx.x == 32) DBG_MARK(6);
 }
@@ -598,6 +615,14 @@ int make_map_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const 
     return 0;
 }
 
+bool gemm_cluster_enabled() {
+    static const bool on = []() {
+        const char* e = getenv("DTP_CLUSTER");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static void params_defaults(GemmParams& p) {
     memset(&p, 0, sizeof(p));
     p.splits = 1;
@@ -653,6 +678,11 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
         if (r) return r;
     } else {
         op->mapA1 = op->mapA0;
+    }
+    op->cluster = 1;
+    if (!w_blocked && gemm_cluster_enabled() && op->grid_m >= 2 && BN >= 32) {
+        if (map_rows(&op->mapBh, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN / 2)) return -13;
+        op->cluster = 2;
     }
     if (w_blocked) {
         const int K = K0 + (A1 ? K1 : 0);
@@ -720,6 +750,11 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     } else {
         op->mapA1 = op->mapA0;
     }
+    op->cluster = 1;
+    if (!w_blocked && gemm_cluster_enabled() && op->grid_m >= 2 && BN >= 32) {
+        if (map_rows(&op->mapBh, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN / 2)) return -13;
+        op->cluster = 2;
+    }
     if (w_blocked) {
         if ((Cout % 64) != 0 || (BN % 64) != 0) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "blocked conv weights need Cout, BN %% 64 == 0 (Cout=%d BN=%d)", Cout, BN);
@@ -752,6 +787,7 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
     if (b_mn) p.flags |= GEMM_B_MN;
     op->BN = BN;
     op->grid_m = (M + 127) / 128;
+    op->cluster = 1;
     // size-1 batch dims still need a legal (multiple of 16 B) stride
     auto zstride = [](long long s, uint64_t fallback) -> uint64_t { return s > 0 ? (uint64_t)s * 2 : fallback; };
     {
@@ -802,7 +838,7 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
         if (bn >= 64 && bn - 32 >= ((N + 31) / 32) * 32) continue;  // mostly padding
         const long long gn = (N + bn - 1) / bn;
         const double t_mma = 2.0 * bn;
-        const double t_tma = (16384.0 + 128.0 * bn) / 58.0;
+        const double t_tma = (16384.0 + ((flags & GEMM_HINT_CL2) ? 64.0 : 128.0) * bn) / 58.0;
         const double t_kb = t_mma > t_tma ? t_mma : t_tma;
         const double t_epi = 300.0 + (bn / 32) * 350.0;
         const int max_sp = (flags & GEMM_B_MN) ? 1 : 16;
@@ -815,7 +851,8 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
             const double t_tile = (t_main > t_epi_eff ? t_main : t_epi_eff) + 200.0;
             const double per_cta = static_cast<double>((tiles + kSMs - 1) / kSMs);
             double cost = per_cta * t_tile + t_epi_eff + 1500.0;
-            const double l2_bytes = static_cast<double>(mtiles) * gn * num_kb * (16384.0 + 128.0 * bn);
+            const double l2_bytes = static_cast<double>(mtiles) * gn * num_kb *
+                                    (16384.0 + ((flags & GEMM_HINT_CL2) ? 64.0 : 128.0) * bn);
             const double t_l2 = l2_bytes / 7000.0;
             if (t_l2 > cost) cost = t_l2;
             if (sp > 1) cost += 2000.0 + rows * N * 4.0 * (sp + 1) / 2500.0;
@@ -849,7 +886,9 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return -20;
@@ -864,15 +903,39 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     p.dbg_mode = dbgmode;
     p.grid_m = op->grid_m;
     p.grid_n = (p.N + BN - 1) / BN;
-    const long long tiles = static_cast<long long>(p.grid_m) * p.grid_n * p.nz1 * p.nz2 * p.splits;
+    const int cl = op->cluster == 2 ? 2 : 1;
+    const long long gm = cl == 2 ? (p.grid_m + 1) / 2 : p.grid_m;
+    const long long tiles = gm * p.grid_n * p.nz1 * p.nz2 * p.splits;  // cluster mode: pairs of m-tiles
     if (tiles > 0x7fffffffLL) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "too many tiles");
         return -24;
     }
     p.total_tiles = static_cast<int>(tiles);
-    const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-    launch_k(gemm_tc_kernel<BN, STAGES>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (cl == 2) {
+        const int max_clusters = num_sms() / 2;
+        const int nclusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * nclusters);
+        cfg.blockDim = dim3(320);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, 2>, op->mapA0, op->mapA1, op->mapBh, p);
+    } else {
+        const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+        e = launch_k(gemm_tc_kernel<BN, STAGES, 1>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
+    }
+    if (e != cudaSuccess) e = cudaGetLastError();
+    else e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch: %s", cudaGetErrorString(e));
         return -21;

@@ -31,6 +31,7 @@ enum GemmFlags : int {
     EPI_IMG01 = 1 << 6,         // out = clamp(x / 2 + 0.5, 0, 1)   (inpaint_pipeline.py:148)
     EPI_OUT_F32 = 1 << 7,       // fp32 row-major output
     GEMM_B_MN = 1 << 8,         // B operand is MN-major in global memory: B[K, N] row-major (V of attention)
+    GEMM_HINT_CL2 = 1 << 11,    // heuristic hint only: the op will run as 2-CTA clusters sharing the weight tile by TMA multicast
     GEMM_W_BLOCKED = 1 << 10,   // weights stored as [N/64][K/64][64][64] tiles (8 KB contiguous per 64x64 block: DRAM-burst friendly)
     EPI_SOFTMAX16 = 1 << 9,     // row softmax over the first `aux` columns of every 16-column group (folded cross-attention)
 };
@@ -68,6 +69,8 @@ struct GemmParams {
 
 struct GemmOp {
     CUtensorMap mapA0, mapA1, mapB;
+    CUtensorMap mapBh;  // B map with a BN/2-row box: each CTA of a 2-CTA cluster fetches one half and multicasts it
+    int cluster;        // 1 or 2
     GemmParams p;
     int BN;      // 32, 64, 128, 160, 192 or 256
     int grid_m;  // number of 128-row tiles
@@ -96,5 +99,7 @@ size_t gemm_workspace_bytes(const GemmOp* op);
 // heuristic tile / split selection for a problem with `mtiles` 128-row tiles
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits);
 const char* gemm_last_error();
+// true when linear / conv problems with >= 2 m-tiles run as 2-CTA clusters (DTP_CLUSTER=0 disables)
+bool gemm_cluster_enabled();
 
 }  // namespace dtp

@@ -219,7 +219,8 @@ struct Builder {
         GemmOp op;
         int BN, splits;
         const int kb = (a.K0 + 63) / 64 + (a.A1 ? (a.K1 + 63) / 64 : 0);
-        gemm_pick_config(static_cast<int>((a.M + 127) / 128), a.N, kb, a.flags, &BN, &splits);
+        const int mt = static_cast<int>((a.M + 127) / 128);
+        gemm_pick_config(mt, a.N, kb, a.flags | ((mt >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
         if (gemm_setup_linear(&op, a.A0, a.lda0, a.K0, a.A1, a.lda1, a.K1, static_cast<int>(a.M), a.W, a.ldw, a.N, BN,
                               splits)) {
             fail(std::string("linear setup: ") + gemm_last_error());
@@ -301,7 +302,8 @@ struct Builder {
             return;
         }
         int BN, splits;
-        gemm_pick_config(probe.grid_m, cout, probe.p.num_kb, flags, &BN, &splits);
+        gemm_pick_config(probe.grid_m, cout, probe.p.num_kb,
+                         flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
         if (gemm_setup_conv3x3(&op, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, BN, splits)) {
             fail(std::string("conv setup: ") + gemm_last_error());
             return;
@@ -1606,15 +1608,24 @@ int Engine::run_graphed(GraphSlot& slot, const std::string& key, const std::func
         ++slot.warm;
         return body(st);
     }
+    // capture and replay on an engine-owned stream (the caller's may be the legacy default stream, which cannot be captured);
+    // events order it after the caller's staging copies and the caller's stream after the replay
+    if (!gstream_) {
+        if (cudaStreamCreateWithFlags(&gstream_, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&gev_in_, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&gev_out_, cudaEventDisableTiming) != cudaSuccess)
+            return fail("graph stream / event creation failed");
+    }
     if (!slot.exec) {
         const long long before = launches_;
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaStreamSynchronize(st);
+        if (cudaStreamBeginCapture(gstream_, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
             cudaGetLastError();
             return body(st);
         }
-        const int rc = body(st);
+        const int rc = body(gstream_);
         cudaGraph_t g = nullptr;
-        const cudaError_t e = cudaStreamEndCapture(st, &g);
+        const cudaError_t e = cudaStreamEndCapture(gstream_, &g);
         if (rc != 0 || e != cudaSuccess || g == nullptr) {
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
@@ -1630,7 +1641,11 @@ int Engine::run_graphed(GraphSlot& slot, const std::string& key, const std::func
         }
         cudaGraphDestroy(g);
     }
-    if (cudaGraphLaunch(slot.exec, st) != cudaSuccess) return fail("cudaGraphLaunch failed");
+    if (cudaEventRecord(gev_in_, st) != cudaSuccess || cudaStreamWaitEvent(gstream_, gev_in_, 0) != cudaSuccess)
+        return fail("graph stream ordering failed");
+    if (cudaGraphLaunch(slot.exec, gstream_) != cudaSuccess) return fail("cudaGraphLaunch failed");
+    if (cudaEventRecord(gev_out_, gstream_) != cudaSuccess || cudaStreamWaitEvent(st, gev_out_, 0) != cudaSuccess)
+        return fail("graph stream ordering failed");
     launches_ += slot.launches;
     ++graph_launches_;
     return 0;

@@ -217,6 +217,8 @@ class Engine {
         long long launches = 0;
     };
     GraphSlot g_infer_, g_stamp_;
+    cudaStream_t gstream_ = nullptr;
+    cudaEvent_t gev_in_ = nullptr, gev_out_ = nullptr;
     int run_graphed(GraphSlot& slot, const std::string& key, const std::function<int(cudaStream_t)>& body,
                     cudaStream_t st);
     std::string schedule_key() const;
