@@ -241,8 +241,11 @@ template <int BN, int STAGES, int CL>
 __global__ void __launch_bounds__(320, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
+    // CL == 2: CTA pair (cta_group::2). One MMA spans both SMs (M = 256); each CTA's shared memory holds its own 128 rows
+    // of A and HALF of the B tile (rows [rank*BN/2, +BN/2)), which halves the shared-memory traffic per CTA - the limit of
+    // the single-CTA mainloop (TMA write + MMA read of A and B exceed 128 B/clk for wide tiles).
     constexpr int A_BYTES = 128 * 128;
-    constexpr int B_BYTES = BN * 128;
+    constexpr int B_BYTES = (BN / CL) * 128;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     constexpr int B_CHUNKS = (BN + 63) / 64;  // MN-major B: 64-column boxes
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(320, 1)
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* peer_full_bar = tmem_empty_bar + 2;   // [STAGES] leader only: the peer CTA's operands of a stage have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full_bar + STAGES);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
 
     const int warp = threadIdx.x >> 5;
@@ -273,18 +277,24 @@ __global__ void __launch_bounds__(320, 1)
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CL);  // CL == 2: both CTAs of the cluster must have consumed the shared B stage
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&peer_full_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
+            mbar_init(&tmem_empty_bar[a], 8 * CL);  // one arrival per epilogue warp (of both CTAs in pair mode)
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
+    if (warp == 1) {
+        if (CL == 2)
+            tmem_alloc2(tmem_slot, TM_COLS);
+        else
+            tmem_alloc(tmem_slot, TM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();  // the peer's barriers must exist before anything is multicast into it
+    if (CL == 2) cluster_sync_all();  // the peer's barriers must exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) DBG_MARK(1);
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(320, 1)
             // STAGES tiles are requested BEFORE waiting for the predecessor kernel, hiding the DRAM latency of
             // weight-streaming layers behind the previous kernel's tail. Activations (A) are only touched after the wait.
             int pre = 0;
-            constexpr int BH = BN / CL;  // rows of the B tile this CTA fetches (CL == 2: its half, multicast to both)
+            constexpr int BH = BN / CL;  // rows of the B tile this CTA fetches (pair mode: its half)
             if (!p.b_batched && !b_mn && tile0 < total_tiles) {
                 const TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
                 pre = min(STAGES, c0.kb_end - c0.kb_begin);
@@ -308,8 +318,7 @@ __global__ void __launch_bounds__(320, 1)
                     mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
                     uint8_t* sbp = smem + s * STAGE_BYTES + A_BYTES;
                     if (CL == 2)
-                        tma_load_4d_mc(sbp + rank * BH * 128, &mapB, &full_bar[s], (c0.kb_begin + s) * 64,
-                                       c0.n0 + rank * BH, 0, 0, 3);
+                        tma_load_4d(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0 + rank * BH, 0, 0);
                     else if (w_blocked)
                         tma_load_4d(sbp, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
                     else
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(320, 1)
                     if (prefetched) {
                         // B tile of this stage is already in flight
                     } else if (CL == 2) {
-                        tma_load_4d_mc(sb + rank * BH * 128, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0, 3);
+                        tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0);
                     } else if (w_blocked) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
@@ -365,9 +374,25 @@ __global__ void __launch_bounds__(320, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------ MMA issuer ------------------------------
-            const uint32_t idesc = umma_idesc_f16(128, BN, 0, b_mn ? 1 : 0);
+        if (lane == 0 && CL == 2 && rank == 1) {
+            // ------------------------------ peer CTA: forward "my operands have landed" to the leader ----------------
+            pdl_wait();
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = tile0; t < total_tiles; t += tstep) {
+                const TileCoord c = decode_tile<BN, CL>(p, t, rank);
+                for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
+                    mbar_wait_bounded(&full_bar[stage], phase);
+                    mbar_arrive_remote(&peer_full_bar[stage], 0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            // ------------------------------ MMA issuer (leader CTA in pair mode) ------------------------------
+            const uint32_t idesc = umma_idesc_f16(128 * CL, BN, 0, b_mn ? 1 : 0);
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
@@ -381,6 +406,7 @@ __global__ void __launch_bounds__(320, 1)
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
                     mbar_wait_bounded(&full_bar[stage], phase);
+                    if (CL == 2) mbar_wait_bounded(&peer_full_bar[stage], phase);
                     if (first) {
                         DBG_MARK(2);
                         first = false;
@@ -395,10 +421,13 @@ __global__ void __launch_bounds__(320, 1)
                         // advance 16 K-elements: 32 B inside the swizzle atom (K-major) / two 8-row groups (MN-major)
                         const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
                         const uint64_t bd = bdesc + static_cast<uint64_t>(b_mn ? k * 128 : k * 2);
-                        umma_f16(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
+                        if (CL == 2)
+                            umma_f16_2cta(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
+                        else
+                            umma_f16(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
                     }
                     if (CL == 2)
-                        umma_commit_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the cluster
+                        umma_commit2_mc(&empty_bar[stage], 3);  // frees the stage in both CTAs of the pair
                     else
                         umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
@@ -406,7 +435,10 @@ __global__ void __launch_bounds__(320, 1)
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                if (CL == 2)
+                    umma_commit2_mc(&tmem_full_bar[acc], 3);  // wakes the epilogue warps of both CTAs
+                else
+                    umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -458,7 +490,12 @@ __global__ void __launch_bounds__(320, 1)
                 // nothing to read for this warp in this tile: still hand the accumulator back
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) {
+                    if (CL == 2 && rank == 1)
+                        mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                    else
+                        mbar_arrive(&tmem_empty_bar[acc]);
+                }
             }
 #pragma unroll 1
             for (int cc = 32 * half, it = 0; it < n_mine; cc += 64, ++it) {
@@ -474,7 +511,12 @@ __global__ void __launch_bounds__(320, 1)
                     // last chunk of this tile is in registers: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) {
+                        if (CL == 2 && rank == 1)
+                            mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                        else
+                            mbar_arrive(&tmem_empty_bar[acc]);
+                    }
                 }
                 if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
                     float v[32];
@@ -510,8 +552,13 @@ __global__ void __launch_bounds__(320, 1)
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
-    if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
+    if (CL == 2) cluster_sync_all();  // no CTA may exit while its peer can still arrive on its barriers / read its operands
+    if (warp == 1) {
+        if (CL == 2)
+            tmem_dealloc2(tmem_base, TM_COLS);
+        else
+            tmem_dealloc(tmem_base, TM_COLS);
+    }
     if (threadIdx.x == 32) DBG_MARK(6);
 }
 
@@ -878,17 +925,17 @@ static int num_sms() {
     return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int STAGES2>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
-    constexpr int STAGE_BYTES = 128 * 128 + BN * 128;
-    constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
-    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
+    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
+    static_assert(SMEM <= 227 * 1024 && SMEM2 <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
         if (e != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return -20;
@@ -918,7 +965,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * nclusters);
         cfg.blockDim = dim3(320);
-        cfg.dynamicSmemBytes = SMEM;
+        cfg.dynamicSmemBytes = SMEM2;
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -929,7 +976,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, 2>, op->mapA0, op->mapA1, op->mapBh, p);
+        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, p);
     } else {
         const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
         e = launch_k(gemm_tc_kernel<BN, STAGES, 1>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
@@ -951,12 +998,12 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
     }
     int r;
     switch (op->BN) {
-        case 32: r = launch_cfg<32, 8>(op, stream); break;
-        case 64: r = launch_cfg<64, 8>(op, stream); break;
-        case 128: r = launch_cfg<128, 6>(op, stream); break;
-        case 160: r = launch_cfg<160, 5>(op, stream); break;
-        case 192: r = launch_cfg<192, 5>(op, stream); break;
-        default: r = launch_cfg<256, 4>(op, stream); break;
+        case 32: r = launch_cfg<32, 8, 8>(op, stream); break;
+        case 64: r = launch_cfg<64, 8, 8>(op, stream); break;
+        case 128: r = launch_cfg<128, 6, 8>(op, stream); break;
+        case 160: r = launch_cfg<160, 5, 7>(op, stream); break;
+        case 192: r = launch_cfg<192, 5, 7>(op, stream); break;
+        default: r = launch_cfg<256, 4, 6>(op, stream); break;
     }
     if (r) return r;
     if (p.splits > 1) {
