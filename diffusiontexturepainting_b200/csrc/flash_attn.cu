@@ -611,6 +611,281 @@ static int launch_flash2(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
     return launch_k(flash_attn2_kernel<DCH, KS>, grid, dim3(384), SMEM, st, mq, mk, mv, p) == cudaSuccess ? 0 : -1;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Variant 3: one softmax warpgroup (128 queries per CTA) with TWO score buffers in TMEM: S_{j+1} = Q K_{j+1}^T is issued
+// while the warpgroup is still exponentiating block j, so the tensor pipe never sits on the softmax critical path; the
+// 128 scores of a row are read from TMEM once and stay in registers (setmaxnreg).  TMEM: S[0] | S[1] | O (<= 160 columns).
+// Warps 0-3: softmax, warp 4: TMA producer, warp 5: MMA issuer, warps 6-7 idle (complete the control warpgroup).
+// ------------------------------------------------------------------------------------------------------------
+template <int DCH, int KS>
+__global__ void __launch_bounds__(256, 1)
+    flash_attn3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ FlashParams p) {
+    constexpr int TILE_BYTES = DCH * 16384;
+    constexpr int P_BYTES = 2 * 16384;
+    constexpr uint32_t O_COL = 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sK + KS * TILE_BYTES;
+    uint8_t* sP = sV + KS * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;
+    uint64_t* k_empty = k_full + KS;
+    uint64_t* v_full = k_empty + KS;
+    uint64_t* v_empty = v_full + KS;
+    uint64_t* s_full = v_empty + KS;  // [2]
+    uint64_t* s_free = s_full + 2;    // [2]
+    uint64_t* p_full = s_free + 2;
+    uint64_t* o_done = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+    const int nblk = (p.seq_kv + 127) / 128;
+
+    pdl_launch_dependents();
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&mapQ);
+        tma_prefetch_desc(&mapK);
+        tma_prefetch_desc(&mapV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < KS; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 4);
+        }
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp >= 4) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+#pragma unroll
+            for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * 16384, &mapQ, q_full, c * 64, q0, head, b);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < nblk; ++j) {
+                fa_wait(&k_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sK + st * TILE_BYTES + c * 16384, &mapK, &k_full[st], c * 64, j * 128, head, b);
+                fa_wait(&v_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+#pragma unroll
+                for (int c = 0; c < DCH; ++c)
+                    tma_load_4d(sV + st * TILE_BYTES + c * 16384, &mapV, &v_full[st], c * 64, j * 128, head, b);
+                if (++st == KS) {
+                    st = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+      } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
+            const uint32_t idesc_o = umma_idesc_f16(128, p.dN, 0, 1);
+            const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+            fa_wait(q_full, 0);
+            int kst = 0, vst = 0;
+            uint32_t kph = 0, vph = 0;
+            // scores of block jj into buffer jj & 1 (the softmax must have copied block jj - 2 out of that buffer)
+            auto issue_s = [&](int jj) {
+                fa_wait(&k_full[kst], kph);
+                if (jj >= 2) fa_wait(&s_free[jj & 1], ((jj >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + kst * TILE_BYTES);
+                for (int kk = 0; kk < p.ksteps_qk; ++kk) {
+                    const uint32_t off = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base + (jj & 1) * 128, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off),
+                             idesc_s, kk > 0 ? 1u : 0u);
+                }
+                umma_commit(&k_empty[kst]);
+                umma_commit(&s_full[jj & 1]);
+                if (++kst == KS) {
+                    kst = 0;
+                    kph ^= 1;
+                }
+            };
+            issue_s(0);
+            for (int j = 0; j < nblk; ++j) {
+                if (j + 1 < nblk) issue_s(j + 1);  // overlaps the softmax of block j
+                fa_wait(&v_full[vst], vph);
+                fa_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sV + vst * TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t poff = static_cast<uint32_t>((kk >> 2) * 16384 + (kk & 3) * 32);
+                    umma_f16(tmem_base + O_COL, umma_desc_k_sw128(p_addr + poff),
+                             umma_desc_mn_sw128(v_addr + static_cast<uint32_t>(kk) * 2048u, 16384), idesc_o,
+                             (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(&v_empty[vst]);
+                umma_commit(o_done);
+                if (++vst == KS) {
+                    vst = 0;
+                    vph ^= 1;
+                }
+            }
+        }
+      }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t o_col = tmem_base + t_lane + O_COL;
+        float m_used = -INFINITY, l = 0.0f;
+        uint8_t* prow = sP + r * 128;
+        const int sw = r & 7;
+        const float sc = p.scale_log2;
+        for (int j = 0; j < nblk; ++j) {
+            fa_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const int kv_valid = min(128, p.seq_kv - j * 128);
+            const uint32_t s_col = tmem_base + t_lane + (j & 1) * 128;
+            uint32_t raw[128];
+#pragma unroll
+            for (int c = 0; c < 128; c += 32) tmem_ld_32x32(s_col + c, *reinterpret_cast<uint32_t(*)[32]>(&raw[c]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[j & 1]);
+            float bm = -INFINITY;
+            if (kv_valid == 128) {
+                float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 128; i += 4) {
+                    b0 = fmaxf(b0, __uint_as_float(raw[i]));
+                    b1 = fmaxf(b1, __uint_as_float(raw[i + 1]));
+                    b2 = fmaxf(b2, __uint_as_float(raw[i + 2]));
+                    b3 = fmaxf(b3, __uint_as_float(raw[i + 3]));
+                }
+                bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    if (i >= kv_valid) raw[i] = 0xff800000u;
+                    bm = fmaxf(bm, __uint_as_float(raw[i]));
+                }
+            }
+            bm *= sc;
+            if (j > 0) fa_wait(o_done, (j - 1) & 1);
+            tc_fence_after();
+            bool need = false;
+            float factor = 1.0f;
+            if (j == 0) {
+                m_used = bm;
+            } else if (bm > m_used + 8.0f) {
+                need = true;
+                factor = ex2_approx(m_used - bm);
+                m_used = bm;
+            }
+            if (__any_sync(0xffffffffu, need)) {
+                l *= factor;
+                for (int c = 0; c < p.dN; c += 32) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(o_col + c, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                    tmem_st_32x32(o_col + c, o);
+                }
+                tmem_st_wait();
+            }
+            const float neg_m = -m_used;
+            float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 128; c += 8) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
+                l0 += (e[0] + e[1]) + (e[2] + e[3]);
+                l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
+                __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
+                uint4 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0);
+                u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2);
+                u.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(prow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = u;
+            }
+            l += l0 + l1;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        fa_wait(o_done, (nblk - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const int row = q0 + r;
+        __half* orow = p.out + b * p.o_bs + static_cast<long long>(row) * p.ldo + head * p.d;
+        for (int c = 0; c < p.dN; c += 32) {
+            uint32_t raw[32];
+            tmem_ld_32x32(o_col + c, raw);
+            tmem_ld_wait();
+            if (row < p.seq_q) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    if (c + i + 8 <= p.d) {
+                        __half2 h0 = __floats2half2_rn(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv);
+                        __half2 h1 = __floats2half2_rn(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv);
+                        __half2 h2 = __floats2half2_rn(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv);
+                        __half2 h3 = __floats2half2_rn(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv);
+                        uint4 u;
+                        u.x = *reinterpret_cast<uint32_t*>(&h0);
+                        u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2);
+                        u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(orow + c + i) = u;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+template <int DCH, int KS>
+static int launch_flash3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashParams& p,
+                         cudaStream_t st) {
+    constexpr int SMEM = DCH * 16384 * (1 + 2 * KS) + 2 * 16384 + (8 + 4 * KS) * 8 + 16 + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(flash_attn3_kernel<DCH, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+            cudaSuccess)
+            return -1;
+        attr_set = true;
+    }
+    dim3 grid((p.seq_q + 127) / 128, p.heads, p.batch);
+    return launch_k(flash_attn3_kernel<DCH, KS>, grid, dim3(256), SMEM, st, mq, mk, mv, p) == cudaSuccess ? 0 : -1;
+}
+
 template <int DCH, int KV_STAGES>
 static int launch_flash(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FlashParams& p,
                         cudaStream_t st) {
@@ -673,7 +948,17 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
         const char* e = getenv("DTP_FLASH2");
         return !(e && e[0] == '0');
     }();
-    if (two_wg && op->seq >= 256 && op->d <= 64)
+    static const int variant = []() {
+        const char* e = getenv("DTP_FLASH_VARIANT");
+        return e ? atoi(e) : 3;
+    }();
+    if (variant == 3 && op->seq >= 128 && op->d <= 64)
+        r = launch_flash3<1, 2>(op->mq, op->mk, op->mv, p, st);
+    else if (variant == 3 && op->seq >= 128 && op->d <= 128)
+        r = launch_flash3<2, 2>(op->mq, op->mk, op->mv, p, st);
+    else if (variant == 3 && op->seq >= 128)
+        r = launch_flash3<3, 1>(op->mq, op->mk, op->mv, p, st);
+    else if (two_wg && op->seq >= 256 && op->d <= 64)
         r = launch_flash2<1, 2>(op->mq, op->mk, op->mv, p, st);
     else if (two_wg && op->seq >= 256 && op->d <= 128)
         r = launch_flash2<2, 1>(op->mq, op->mk, op->mv, p, st);
