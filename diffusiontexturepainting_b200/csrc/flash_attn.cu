@@ -950,7 +950,7 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
     }();
     static const int variant = []() {
         const char* e = getenv("DTP_FLASH_VARIANT");
-        return e ? atoi(e) : 3;
+        return e ? atoi(e) : 2;
     }();
     if (variant == 3 && op->seq >= 128 && op->d <= 64)
         r = launch_flash3<1, 2>(op->mq, op->mk, op->mv, p, st);
