@@ -162,10 +162,23 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     float* stat = reinterpret_cast<float*>(sm_acc);  // [groups][2] mean, rstd
     if (threadIdx.x < groups) {
         double a = 0.0, b = 0.0;
-        const volatile float* pp = partial + (static_cast<long long>(n) * chunks * groups + threadIdx.x) * 2;
-        for (int ch = 0; ch < chunks; ++ch) {
-            a += static_cast<double>(pp[static_cast<long long>(ch) * groups * 2]);
-            b += static_cast<double>(pp[static_cast<long long>(ch) * groups * 2 + 1]);
+        // L2 loads (the partials were written by other CTAs; __threadfence + ticket order them), 8 in flight per thread
+        const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * groups + threadIdx.x;
+        int ch = 0;
+        for (; ch + 8 <= chunks; ch += 8) {
+            float2 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(pp + static_cast<long long>(ch + u) * groups);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a += static_cast<double>(t[u].x);
+                b += static_cast<double>(t[u].y);
+            }
+        }
+        for (; ch < chunks; ++ch) {
+            const float2 t = __ldcg(pp + static_cast<long long>(ch) * groups);
+            a += static_cast<double>(t.x);
+            b += static_cast<double>(t.y);
         }
         const double count = static_cast<double>(HW) * cpg;
         const double mean = a / count;
