@@ -2,6 +2,7 @@
 #include "kernels.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -60,7 +61,9 @@ int gn_num_chunks(int HW, int C) {
     return static_cast<int>(chunks);
 }
 size_t gn_ws_floats(int Nimg, int HW, int C, int groups) {
-    return static_cast<size_t>(Nimg) * gn_num_chunks(HW, C) * groups * 2 + static_cast<size_t>(Nimg) * C * 2 + 64;
+    int chunks = gn_num_chunks(HW, C);
+    if (chunks < 160) chunks = 160;  // the single-launch path publishes one partial per CTA (<= #SMs per sample)
+    return static_cast<size_t>(Nimg) * chunks * groups * 2 + static_cast<size_t>(Nimg) * C * 2 + 64;
 }
 
 static int* g_gn_counters = nullptr;  // self-resetting per-sample tickets (stream-ordered reuse)
@@ -304,6 +307,222 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Single-launch GroupNorm for tensors that fit the SMs' shared memory (every UNet GroupNorm at B <= 4): the CTAs of a sample
+// keep their row slab in smem, publish per-group partial sums, meet at a per-sample barrier (all CTAs are co-resident:
+// grid <= #SMs, one CTA per SM), fold the partials in a fixed order and normalise straight out of smem. The tensor is
+// read from L2/HBM once and there is one launch instead of two.
+//   barrier state per sample: {arrive count, generation}; the generation is read before arriving, so replaying the same
+//   launch (CUDA graph) needs no host-side reset.
+static unsigned* g_gn_barrier = nullptr;
+static int gn_barrier_state(int Nimg, unsigned** out) {
+    static int cap = 0;
+    if (Nimg > cap) {
+        if (g_gn_barrier) cudaFree(g_gn_barrier);
+        cap = Nimg < 256 ? 256 : Nimg;
+        if (cudaMalloc(&g_gn_barrier, cap * 2 * sizeof(unsigned)) != cudaSuccess) {
+            cap = 0;
+            g_gn_barrier = nullptr;
+            return -1;
+        }
+        cudaMemset(g_gn_barrier, 0, cap * 2 * sizeof(unsigned));
+    }
+    *out = g_gn_barrier;
+    return 0;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// grid (cps, Nimg); block = CV * rows_per_iter threads; dynamic smem = slab [rpc][C] fp16 | acc [rows_per_iter][C] float2
+__global__ void __launch_bounds__(512)
+    gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
+                    int rpc, float* __restrict__ partial, unsigned* __restrict__ barrier,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                    __half* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char gn_smem[];
+    __shared__ double s_red[16][32][2];
+    __shared__ float s_stat[256][2];
+    __shared__ unsigned s_gen;
+    const int C = C0 + C1;
+    const int CV = C >> 3;
+    const int cv = threadIdx.x % CV;
+    const int prow = threadIdx.x / CV;
+    const int rows_per_iter = blockDim.x / CV;
+    const int n = blockIdx.y;
+    const int cps = gridDim.x;
+    const int p0 = blockIdx.x * rpc;
+    const int p1 = min(HW, p0 + rpc);
+    const int c = cv * 8;
+    __half* slab = reinterpret_cast<__half*>(gn_smem);
+    float2* acc = reinterpret_cast<float2*>(gn_smem + static_cast<size_t>(rpc) * C * sizeof(__half));
+    const __half* src;
+    int ldc;
+    if (c < C0) {
+        src = x0 + static_cast<long long>(n) * HW * C0 + c;
+        ldc = C0;
+    } else {
+        src = x1 + static_cast<long long>(n) * HW * C1 + (c - C0);
+        ldc = C1;
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) s_gen = ld_acquire_u32(barrier + 2 * n + 1);
+    float s[8], ss[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.0f;
+    int p = p0 + prow;
+    for (; p + 3 * rows_per_iter < p1; p += 4 * rows_per_iter) {
+        Half8 h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) h[u] = ld8(src + static_cast<long long>(p + u * rows_per_iter) * ldc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            st8(slab + static_cast<size_t>(p + u * rows_per_iter - p0) * C + c, h[u]);
+            float f[8];
+            unpack8(h[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += f[e];
+                ss[e] = fmaf(f[e], f[e], ss[e]);
+            }
+        }
+    }
+    for (; p < p1; p += rows_per_iter) {
+        const Half8 h = ld8(src + static_cast<long long>(p) * ldc);
+        st8(slab + static_cast<size_t>(p - p0) * C + c, h);
+        float f[8];
+        unpack8(h, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s[e] += f[e];
+            ss[e] = fmaf(f[e], f[e], ss[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[prow * C + c + e] = make_float2(s[e], ss[e]);
+    __syncthreads();
+    // per-channel sums over the thread rows, then per-group sums (fixed order)
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        float2 t = acc[ch];
+        for (int r = 1; r < rows_per_iter; ++r) {
+            const float2 u = acc[r * C + ch];
+            t.x += u.x;
+            t.y += u.y;
+        }
+        acc[ch] = t;
+    }
+    __syncthreads();
+    const int cpg = C / groups;
+    if (threadIdx.x < groups) {
+        float a = 0.0f, b = 0.0f;
+        for (int cc = 0; cc < cpg; ++cc) {
+            const float2 t = acc[threadIdx.x * cpg + cc];
+            a += t.x;
+            b += t.y;
+        }
+        reinterpret_cast<float2*>(partial)[(static_cast<long long>(n) * cps + blockIdx.x) * groups + threadIdx.x] =
+            make_float2(a, b);
+    }
+    // per-sample barrier
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = s_gen;
+        const unsigned prev = atomicAdd(barrier + 2 * n, 1u);
+        if (prev == static_cast<unsigned>(cps - 1)) {
+            barrier[2 * n] = 0u;
+            __threadfence();
+            st_release_u32(barrier + 2 * n + 1, gen + 1u);
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(barrier + 2 * n + 1) == gen) {
+                if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a CTA of this grid never became resident
+            }
+        }
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    // fold the partials of all CTAs of this sample: thread (slice q, group g) sums j = q, q+16, ... then slices in order
+    {
+        const int g = threadIdx.x % 32, q = threadIdx.x / 32;
+        const int nq = min(16, static_cast<int>(blockDim.x / 32));
+        for (int gb = 0; gb < groups; gb += 32) {
+            if (q < nq) {
+                double a = 0.0, b = 0.0;
+                if (gb + g < groups) {
+                    const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * cps * groups + gb + g;
+                    for (int j = q; j < cps; j += nq) {
+                        const float2 t = __ldcg(pp + static_cast<long long>(j) * groups);
+                        a += static_cast<double>(t.x);
+                        b += static_cast<double>(t.y);
+                    }
+                }
+                s_red[q][g][0] = a;
+                s_red[q][g][1] = b;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32 && gb + g < groups) {
+                double a = 0.0, b = 0.0;
+                for (int r = 0; r < nq; ++r) {
+                    a += s_red[r][g][0];
+                    b += s_red[r][g][1];
+                }
+                const double count = static_cast<double>(HW) * cpg;
+                const double mean = a / count;
+                double var = b / count - mean * mean;
+                if (var < 0.0) var = 0.0;
+                s_stat[gb + g][0] = static_cast<float>(mean);
+                s_stat[gb + g][1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+            }
+            __syncthreads();
+        }
+    }
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int ch = c + e;
+        const int g = ch / cpg;
+        sc[e] = s_stat[g][1] * __ldg(gamma + ch);
+        sh[e] = __ldg(beta + ch) - s_stat[g][0] * sc[e];
+    }
+    __half* dst = out + static_cast<long long>(n) * HW * C + c;
+    for (p = p0 + prow; p < p1; p += rows_per_iter) {
+        float f[8];
+        unpack8(*reinterpret_cast<const Half8*>(slab + static_cast<size_t>(p - p0) * C + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y = fmaf(f[e], sc[e], sh[e]);
+            if (silu) y = silu_f(y);
+            f[e] = y;
+        }
+        st8(dst + static_cast<long long>(p) * C, pack8(f));
+    }
+}
+
+static int gn_fused_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DTP_GN_FUSED");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+static int gn_sm_count() {
+    static int v = 0;
+    if (!v) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+    }
+    return v;
+}
+
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
                      const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
                      cudaStream_t st) {
@@ -319,6 +538,36 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         return -1;
     }
     const int cpg = C / groups;
+    if (gn_fused_enabled() && CV <= 512 && Nimg <= gn_sm_count()) {
+        int rows_per_iter = 512 / CV;
+        if (rows_per_iter > HW) rows_per_iter = HW;
+        const int threads = CV * rows_per_iter;
+        int cps = gn_sm_count() / Nimg;
+        // keep at least ~8 KB of rows per CTA and no more CTAs than row groups
+        int min_rows = (8192 + C * 2 - 1) / (C * 2);
+        if (min_rows < rows_per_iter) min_rows = rows_per_iter;
+        if (cps > (HW + min_rows - 1) / min_rows) cps = (HW + min_rows - 1) / min_rows;
+        if (cps < 1) cps = 1;
+        const int rpc = (HW + cps - 1) / cps;
+        cps = (HW + rpc - 1) / rpc;
+        const size_t smem = static_cast<size_t>(rpc) * C * sizeof(__half) + static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
+        if (smem <= 200 * 1024 && threads >= 32 && threads >= (groups < 32 ? groups : 32) && threads >= groups) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+                    return check_launch("gn_fused attr");
+                attr_set = true;
+            }
+            unsigned* barrier = nullptr;
+            if (gn_barrier_state(Nimg, &barrier)) {
+                snprintf(g_kerr, sizeof(g_kerr), "groupnorm: barrier allocation failed");
+                return -1;
+            }
+            launch_k(gn_fused_kernel, dim3(cps, Nimg), dim3(threads), smem, st, x0, C0, x1, C1, HW, groups, rpc, stats_ws, barrier,
+                     gamma, beta, eps, silu, out);
+            return check_launch("gn_fused");
+        }
+    }
     const long long pairs = static_cast<long long>(HW) * (cpg / 2);
     if ((cpg % 2) == 0 && pairs <= 256 * 12) {
         dim3 grid(groups, Nimg);

@@ -91,9 +91,14 @@ void Profiler::reset() {
     by_label.clear();
 }
 
+// Measurement aid (dtp_set_option("debug_skip_kinds", mask)): ops whose kind bit is set are not launched, so the in-graph
+// cost of a kernel family is the difference of two stamp times. Results are garbage while it is non-zero.
+static int g_debug_skip_kinds = 0;
+
 int Plan::run(cudaStream_t st, long long* launch_counter, Profiler* prof) const {
     const bool p = prof && prof->on;
     for (size_t i = 0; i < ops.size(); ++i) {
+        if (g_debug_skip_kinds && i < kinds.size() && ((g_debug_skip_kinds >> kinds[i]) & 1)) continue;
         cudaEvent_t a = nullptr, b = nullptr;
         if (p) {
             a = prof->get();
@@ -1837,6 +1842,12 @@ int Engine::set_option(const char* name, int value) {
     if (n == "flash") {
         opt_flash_ = value;
         unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "debug_skip_kinds") {
+        g_debug_skip_kinds = value;
         g_infer_.key.clear();
         g_stamp_.key.clear();
         return 0;

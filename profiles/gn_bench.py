@@ -1,0 +1,75 @@
+"""GroupNorm microbenchmark over the shapes of a 512x512 stamp (3 UNet branches) and of C3 (12 samples at 256x256):
+single-launch smem-resident kernel (default) vs the two-launch stats+apply path (DTP_GN_FUSED=0), back-to-back launches
+on one stream (PDL on), L2-warm.  Also checks repeated launches are bitwise identical (the barrier state is reused).
+    python profiles/gn_bench.py            # run under both settings: DTP_GN_FUSED=0 python profiles/gn_bench.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from diffusiontexturepainting_b200 import _native as nat  # noqa: E402
+
+L = nat.lib()
+dev = "cuda"
+
+SHAPES = [  # (Nimg, HW, C0, C1)
+    (3, 4096, 320, 0), (3, 4096, 320, 320), (3, 4096, 640, 320), (3, 1024, 640, 0), (3, 1024, 640, 640),
+    (3, 1024, 1280, 640), (3, 1024, 320, 0), (3, 256, 1280, 0), (3, 256, 1280, 1280), (3, 256, 640, 0),
+    (3, 64, 1280, 0), (3, 64, 1280, 1280), (12, 1024, 320, 0), (12, 1024, 640, 320), (12, 256, 640, 0),
+    (12, 64, 1280, 1280), (2, 4096, 512, 0), (1, 16384, 512, 0),
+]
+
+
+def run(n, hw, c0, c1):
+    torch.manual_seed(0)
+    x0 = (torch.randn(n, hw, c0, device=dev) * 2 + 0.5).half()
+    x1 = torch.randn(n, hw, c1, device=dev).half() if c1 else None
+    C = c0 + c1
+    g = torch.randn(C, device=dev) * 0.2 + 1
+    b = torch.randn(C, device=dev) * 0.2
+    out = torch.empty(n, hw, C, device=dev, dtype=torch.float16)
+
+    def call():
+        nat.check_op(L.dtp_op_groupnorm(nat.ptr(x0), c0, nat.ptr(x1), c1, n, hw, 32, nat.ptr(g), nat.ptr(b), 1e-5, 1,
+                                        nat.ptr(out), nat.stream_ptr()), "groupnorm")
+    call()
+    torch.cuda.synchronize()
+    first = out.clone()
+    x = torch.cat([x0, x1], 2) if c1 else x0
+    ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1))
+    err = ((out.float() - ref).norm() / ref.norm()).item()
+    for _ in range(5):
+        call()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(first, out))
+    # device-bound time: 50 launches captured into one CUDA graph (PDL edges kept), replayed 4 times
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    reps = 50
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(reps):
+                call()
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(4):
+            graph.replay()
+        e1.record(side)
+    torch.cuda.synchronize()
+    same = same and bool(torch.equal(first, out))
+    return e0.elapsed_time(e1) * 1e3 / (4 * reps), err, same
+
+
+if __name__ == "__main__":
+    print("DTP_GN_FUSED=%s" % os.environ.get("DTP_GN_FUSED", "1"))
+    for shp in SHAPES:
+        us, err, same = run(*shp)
+        n, hw, c0, c1 = shp
+        mb = n * hw * (c0 + c1) * 2 * 2 / 1e6
+        print("N=%2d HW=%5d C=%4d+%4d  %7.2f us  (%.1f MB r+w -> %.0f GB/s)  rel=%.1e  replay_identical=%s"
+              % (n, hw, c0, c1, us, mb, mb / us * 1e3, err, same), flush=True)

@@ -22,6 +22,8 @@ ap.add_argument("--tag", default="r1")
 ap.add_argument("--stamps", type=int, default=1)
 ap.add_argument("--no-op-profile", action="store_true")
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--ablate", action="store_true",
+                help="graph-mode stamp time with each kernel family skipped in turn (in-situ cost = difference)")
 a = ap.parse_args()
 R, S, B = a.resolution, a.denoise_steps, a.batch
 model = TRTConditionalInpainter(R, device=0, model_config=W.sd15_config(), max_batch_size=B)
@@ -35,6 +37,31 @@ out = torch.empty(B, 3, R, R, device="cuda")
 eng = model.engine
 if a.no_graph:
     eng.set_option("graph", 0)
+if a.ablate:
+    KINDS = ["other", "contraction", "groupnorm", "layernorm", "softmax", "attn_small", "flash_attn"]
+
+    def timed(n=4):
+        for _ in range(2):
+            eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    base = timed()
+    print("graph-mode stamp: %.2f ms" % base)
+    for k, name in enumerate(KINDS):
+        if name in ("other", "softmax"):
+            continue
+        eng.set_option("debug_skip_kinds", 1 << k)
+        t = timed()
+        print("  without %-12s %.2f ms  -> in-situ cost %.2f ms" % (name, t, base - t), flush=True)
+    eng.set_option("debug_skip_kinds", 0)
+    sys.exit(0)
 eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
 torch.cuda.synchronize()
 if not a.no_op_profile:
