@@ -59,7 +59,10 @@ const char* dtp_ops_last_error(void) { return g_err; }
 // tuning aid: when set, every contraction launched through the operator entry points records per-CTA globaltimer
 // checkpoints into dbg[cta*8 + slot] (slot 0 start, 1 setup done, 2 first operands landed, 3 MMAs issued,
 // 4 accumulator ready, 5 epilogue done, 6 TMEM released)
-void dtp_ops_set_debug_buffer(long long* dbg) { g_dbg = dbg; }
+void dtp_ops_set_debug_buffer(long long* dbg) {
+    g_dbg = dbg;
+    kernels_set_debug(dbg);
+}
 
 int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, int K1, int M, const void* Wt, int ldw,
                   int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,

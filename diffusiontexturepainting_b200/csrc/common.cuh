@@ -288,7 +288,8 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x): one ex2 + one rcp on the MUFU pipe (no IEEE-division fix-up path); 0 for x < -87
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7): one rcp, one ex2, six FMAs
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
@@ -301,7 +302,31 @@ __device__ __forceinline__ float erf_fast(float x) {
     return copysignf(y, x);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction. A lane that writes its 64..128
+// contiguous bytes as 16-byte pieces leaves half-written sectors between instructions, and L2 then fetches the line from
+// DRAM to merge them (measured: DRAM reads == inputs + OUTPUT size for every contraction launch).
+__device__ __forceinline__ void st_global_v8(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_v8f(float* ptr, float a, float b, float c, float d, float e, float f, float g, float h) {
+    st_global_v8(ptr, __float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d), __float_as_uint(e),
+                 __float_as_uint(f), __float_as_uint(g), __float_as_uint(h));
+}
+__device__ __forceinline__ void ld_global_nc_v8(const void* ptr, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(ptr));
+}
+__device__ __forceinline__ bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31) == 0; }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 // host: launch with the programmatic-stream-serialization attribute (DTP_PDL=0 disables it)
 inline int pdl_enabled() {

@@ -25,25 +25,47 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 __device__ __forceinline__ float quick_gelu_fast(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 
 __device__ __forceinline__ void store_half_chunk(__half* out, const float (&v)[32], int ncols, bool vec_ok) {
-    if (ncols == 32 && vec_ok) {
+    if (ncols == 32 && vec_ok && aligned32(out)) {
+        // 64 bytes per lane as two full-sector stores
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            st_global_v8(out + 16 * i, pack_half2(v[16 * i + 0], v[16 * i + 1]), pack_half2(v[16 * i + 2], v[16 * i + 3]),
+                         pack_half2(v[16 * i + 4], v[16 * i + 5]), pack_half2(v[16 * i + 6], v[16 * i + 7]),
+                         pack_half2(v[16 * i + 8], v[16 * i + 9]), pack_half2(v[16 * i + 10], v[16 * i + 11]),
+                         pack_half2(v[16 * i + 12], v[16 * i + 13]), pack_half2(v[16 * i + 14], v[16 * i + 15]));
+    } else if (ncols == 32 && vec_ok) {
         uint4* o = reinterpret_cast<uint4*>(out);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            __half2 a = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-            __half2 b = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-            __half2 c = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-            __half2 d = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
             uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&a);
-            u.y = *reinterpret_cast<uint32_t*>(&b);
-            u.z = *reinterpret_cast<uint32_t*>(&c);
-            u.w = *reinterpret_cast<uint32_t*>(&d);
+            u.x = pack_half2(v[8 * i + 0], v[8 * i + 1]);
+            u.y = pack_half2(v[8 * i + 2], v[8 * i + 3]);
+            u.z = pack_half2(v[8 * i + 4], v[8 * i + 5]);
+            u.w = pack_half2(v[8 * i + 6], v[8 * i + 7]);
             o[i] = u;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (i < ncols) out[i] = __float2half_rn(v[i]);
+    }
+}
+
+// fp32 chunk (split-K partials, fp32 outputs): 128 bytes per lane as four full-sector stores
+__device__ __forceinline__ void store_f32_chunk(float* out, const float (&v)[32], int ncols, bool vec_ok) {
+    if (ncols == 32 && vec_ok && aligned32(out)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            st_global_v8f(out + 8 * i, v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6],
+                          v[8 * i + 7]);
+    } else if (ncols == 32 && vec_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            reinterpret_cast<float4*>(out)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < ncols) out[i] = v[i];
     }
 }
 
@@ -61,8 +83,18 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     const __half* rp = has_res ? p.residual + res_off + static_cast<long long>(row) * p.ldr + col0 : nullptr;
     const bool res_vec = has_res && ncols == 32 && (p.ldr & 7) == 0;
     if (res_vec) {
+        if (aligned32(rp)) {
+            uint32_t t0[8], t1[8];
+            ld_global_nc_v8(rp, t0);
+            ld_global_nc_v8(rp + 16, t1);
+            rraw[0] = make_uint4(t0[0], t0[1], t0[2], t0[3]);
+            rraw[1] = make_uint4(t0[4], t0[5], t0[6], t0[7]);
+            rraw[2] = make_uint4(t1[0], t1[1], t1[2], t1[3]);
+            rraw[3] = make_uint4(t1[4], t1[5], t1[6], t1[7]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rraw[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+            for (int i = 0; i < 4; ++i) rraw[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+        }
     }
     if (flags & EPI_BIAS_M) {
         const float rb = p.bias ? __ldg(p.bias + row) : 0.0f;
@@ -102,19 +134,18 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
         float o[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = v[i] * gelu_erf_f(v[16 + i]);
-        if ((p.ldc & 7) == 0) {
+        if ((p.ldc & 7) == 0 && aligned32(out)) {
+            st_global_v8(out, pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]),
+                         pack_half2(o[8], o[9]), pack_half2(o[10], o[11]), pack_half2(o[12], o[13]), pack_half2(o[14], o[15]));
+        } else if ((p.ldc & 7) == 0) {
             uint4* d = reinterpret_cast<uint4*>(out);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                __half2 a = __floats2half2_rn(o[8 * i + 0], o[8 * i + 1]);
-                __half2 b = __floats2half2_rn(o[8 * i + 2], o[8 * i + 3]);
-                __half2 c = __floats2half2_rn(o[8 * i + 4], o[8 * i + 5]);
-                __half2 e = __floats2half2_rn(o[8 * i + 6], o[8 * i + 7]);
                 uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&a);
-                u.y = *reinterpret_cast<uint32_t*>(&b);
-                u.z = *reinterpret_cast<uint32_t*>(&c);
-                u.w = *reinterpret_cast<uint32_t*>(&e);
+                u.x = pack_half2(o[8 * i + 0], o[8 * i + 1]);
+                u.y = pack_half2(o[8 * i + 2], o[8 * i + 3]);
+                u.z = pack_half2(o[8 * i + 4], o[8 * i + 5]);
+                u.w = pack_half2(o[8 * i + 6], o[8 * i + 7]);
                 d[i] = u;
             }
         } else {
@@ -168,15 +199,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     }
     if (flags & EPI_OUT_F32) {
         float* out = reinterpret_cast<float*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
-        if (ncols == 32 && (p.ldc & 3) == 0 && (out_off & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(out)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < ncols) out[i] = v[i];
-        }
+        store_f32_chunk(out, v, ncols, (p.ldc & 3) == 0 && (out_off & 3) == 0);
         return;
     }
     __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
@@ -237,8 +260,11 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 
 // Persistent kernel: grid = min(tiles, SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
 // Two TMEM accumulators (BN columns each) let the epilogue of tile i overlap the mainloop of tile i+1.
-template <int BN, int STAGES, int CL>
-__global__ void __launch_bounds__(320, 1)
+// OCC = 2: light configuration (few stages, BN <= 128 -> <= 256 TMEM columns, <= 102 registers) so that two CTAs share an SM:
+// the next kernel's CTAs become resident while this one drains (PDL overlap instead of a kernel-boundary bubble) and two
+// tiles interleave their load latency / mainloop / epilogue on one SM.
+template <int BN, int STAGES, int CL, int OCC = 1>
+__global__ void __launch_bounds__(320, OCC)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
     // CL == 2: CTA pair (cta_group::2). One MMA spans both SMs (M = 256); each CTA's shared memory holds its own 128 rows
@@ -528,16 +554,7 @@ __global__ void __launch_bounds__(320, 1)
                                         static_cast<long long>(p.N) +
                                     c.n0 + cc;
                         const int ncols = min(32, p.N - (c.n0 + cc));
-                        if (ncols == 32 && (p.N & 3) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                reinterpret_cast<float4*>(ws)[i] =
-                                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < ncols) ws[i] = v[i];
-                        }
+                        store_f32_chunk(ws, v, ncols, (p.N & 3) == 0);
                     } else {
                         epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
                     }
@@ -581,7 +598,15 @@ __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const __grid_
     for (int s = 0; s < p.splits; ++s) {
         const float* ws =
             p.workspace + (static_cast<long long>(zb * p.splits + s) * p.M + row) * static_cast<long long>(p.N) + col0;
-        if (ncols == 32 && (p.N & 3) == 0) {
+        if (ncols == 32 && (p.N & 3) == 0 && aligned32(ws)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint32_t t[8];
+                ld_global_nc_v8(ws + 8 * i, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 * i + j] += __uint_as_float(t[j]);
+            }
+        } else if (ncols == 32 && (p.N & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(ws) + i);
@@ -928,6 +953,39 @@ static int num_sms() {
     return n;
 }
 
+template <int BN, int STAGES>
+static int launch_light(const GemmOp* op, cudaStream_t stream) {
+    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
+    static_assert(SMEM <= 113 * 1024 && 2 * BN <= 256, "two CTAs per SM");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+            snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute (light): %s", cudaGetErrorString(cudaGetLastError()));
+            return -20;
+        }
+        attr_set = true;
+    }
+    GemmParams p = op->p;
+    p.dbg_mode = 0;
+    p.grid_m = op->grid_m;
+    p.grid_n = (p.N + BN - 1) / BN;
+    const long long tiles = static_cast<long long>(p.grid_m) * p.grid_n * p.nz1 * p.nz2 * p.splits;
+    if (tiles > 0x7fffffffLL) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "too many tiles");
+        return -24;
+    }
+    p.total_tiles = static_cast<int>(tiles);
+    const int cap = 2 * num_sms();
+    const int grid = static_cast<int>(tiles < cap ? tiles : cap);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch (light): %s", cudaGetErrorString(e));
+        return -21;
+    }
+    return 0;
+}
+
 template <int BN, int STAGES, int STAGES2>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
@@ -999,7 +1057,23 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "split-K gemm without workspace");
         return -22;
     }
+    // light configuration: DTP_GEMM_LIGHT = max k-blocks per tile for which it is used. Off by default: measured neutral
+    // on isolated short-K launches and 1.5 % slower over a whole stamp (profiles/README.md).
+    static const int light_max_kb = []() {
+        const char* e = getenv("DTP_GEMM_LIGHT");
+        return e ? atoi(e) : 0;
+    }();
+    const int kb_per_tile = (p.num_kb + p.splits - 1) / (p.splits > 0 ? p.splits : 1);
+    const bool light = light_max_kb > 0 && op->cluster != 2 && op->BN <= 128 && kb_per_tile <= light_max_kb &&
+                       !(p.flags & GEMM_W_BLOCKED);
     int r;
+    if (light) {
+        switch (op->BN) {
+            case 32: r = launch_light<32, 4>(op, stream); break;
+            case 64: r = launch_light<64, 4>(op, stream); break;
+            default: r = launch_light<128, 3>(op, stream); break;
+        }
+    } else
     switch (op->BN) {
         case 32: r = launch_cfg<32, 8, 8>(op, stream); break;
         case 64: r = launch_cfg<64, 8, 8>(op, stream); break;

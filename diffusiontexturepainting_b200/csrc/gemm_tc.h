@@ -74,6 +74,7 @@ struct GemmOp {
     GemmParams p;
     int BN;      // 32, 64, 128, 160, 192 or 256
     int grid_m;  // number of 128-row tiles
+    int light;   // 1: two-CTAs-per-SM configuration (short K loops, BN <= 128); set by gemm_launch from the problem shape
 };
 
 // Tensor-map helper (driver entry point resolved at run time; no link-time libcuda dependency). 0 on success.

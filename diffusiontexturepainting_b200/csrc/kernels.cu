@@ -11,6 +11,19 @@ namespace dtp {
 static char g_kerr[256] = "";
 const char* kernels_last_error() { return g_kerr; }
 
+static long long* g_kdbg = nullptr;  // per-CTA globaltimer checkpoints of the single-launch GroupNorm (debug aid)
+void kernels_set_debug(long long* dbg) { g_kdbg = dbg; }
+__device__ __forceinline__ long long kgtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KDBG(slot)                                                                                                     \
+    do {                                                                                                               \
+        if (dbg != nullptr && threadIdx.x == 0)                                                                        \
+            dbg[(static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = kgtime();               \
+    } while (0)
+
 static int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -311,8 +324,8 @@ __global__ void __launch_bounds__(256)
 // keep their row slab in smem, publish per-group partial sums, meet at a per-sample barrier (all CTAs are co-resident:
 // grid <= #SMs, one CTA per SM), fold the partials in a fixed order and normalise straight out of smem. The tensor is
 // read from L2/HBM once and there is one launch instead of two.
-//   barrier state per sample: {arrive count, generation}; the generation is read before arriving, so replaying the same
-//   launch (CUDA graph) needs no host-side reset.
+//   barrier state per sample: one monotonically growing arrival counter (see GN_BAR_QUANTUM); replaying the same launch
+//   (CUDA graph) needs no host-side reset.
 static unsigned* g_gn_barrier = nullptr;
 static int gn_barrier_state(int Nimg, unsigned** out) {
     static int cap = 0;
@@ -340,15 +353,16 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 
 // grid (cps, Nimg); block = CV * rows_per_iter threads; dynamic smem = slab [rpc][C] fp16 | acc [rows_per_iter][C] float2
+// Barrier: every launch adds exactly GN_BAR_QUANTUM to the sample's counter (CTA 0 adds the remainder), so the counter
+// is a multiple of the quantum between launches and a CTA derives its target from the value its own arrival returned.
+constexpr unsigned GN_BAR_QUANTUM = 256;
 __global__ void __launch_bounds__(512)
     gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
                     int rpc, float* __restrict__ partial, unsigned* __restrict__ barrier,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                    __half* __restrict__ out) {
+                    __half* __restrict__ out, long long* __restrict__ dbg) {
     extern __shared__ __align__(16) unsigned char gn_smem[];
-    __shared__ double s_red[16][32][2];
     __shared__ float s_stat[256][2];
-    __shared__ unsigned s_gen;
     const int C = C0 + C1;
     const int CV = C >> 3;
     const int cv = threadIdx.x % CV;
@@ -370,18 +384,27 @@ __global__ void __launch_bounds__(512)
         src = x1 + static_cast<long long>(n) * HW * C1 + (c - C0);
         ldc = C1;
     }
+    KDBG(0);
+    // affine parameters do not depend on the producer: fetch them before the dependency wait
+    float ga[8], be[8];
+    {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+        ga[0] = g0.x, ga[1] = g0.y, ga[2] = g0.z, ga[3] = g0.w, ga[4] = g1.x, ga[5] = g1.y, ga[6] = g1.z, ga[7] = g1.w;
+        be[0] = b0.x, be[1] = b0.y, be[2] = b0.z, be[3] = b0.w, be[4] = b1.x, be[5] = b1.y, be[6] = b1.z, be[7] = b1.w;
+    }
     pdl_wait();
-    if (threadIdx.x == 0) s_gen = ld_acquire_u32(barrier + 2 * n + 1);
+    KDBG(1);
     float s[8], ss[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.0f;
     int p = p0 + prow;
-    for (; p + 3 * rows_per_iter < p1; p += 4 * rows_per_iter) {
-        Half8 h[4];
+    for (; p + 7 * rows_per_iter < p1; p += 8 * rows_per_iter) {  // eight 16-byte loads in flight per thread
+        Half8 h[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) h[u] = ld8(src + static_cast<long long>(p + u * rows_per_iter) * ldc);
+        for (int u = 0; u < 8; ++u) h[u] = ld8(src + static_cast<long long>(p + u * rows_per_iter) * ldc);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             st8(slab + static_cast<size_t>(p + u * rows_per_iter - p0) * C + c, h[u]);
             float f[8];
             unpack8(h[u], f);
@@ -404,92 +427,99 @@ __global__ void __launch_bounds__(512)
         }
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[prow * C + c + e] = make_float2(s[e], ss[e]);
+    for (int e = 0; e < 8; e += 2)  // 16-byte stores: consecutive threads are 64 B apart, no bank conflicts beyond the minimum
+        *reinterpret_cast<float4*>(&acc[prow * C + c + e]) = make_float4(s[e], ss[e], s[e + 1], ss[e + 1]);
     __syncthreads();
-    // per-channel sums over the thread rows, then per-group sums (fixed order)
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-        float2 t = acc[ch];
-        for (int r = 1; r < rows_per_iter; ++r) {
-            const float2 u = acc[r * C + ch];
-            t.x += u.x;
-            t.y += u.y;
-        }
-        acc[ch] = t;
-    }
-    __syncthreads();
+    KDBG(2);
+    // per-group sums of this CTA: eight lanes per group walk the group's [rows_per_iter][cpg] accumulators, then a fixed
+    // butterfly (bitwise reproducible); the block size is a multiple of 32, so every warp is complete
     const int cpg = C / groups;
-    if (threadIdx.x < groups) {
+    const int lane8 = threadIdx.x & 7, slot = threadIdx.x >> 3, nslots = blockDim.x >> 3;
+    for (int gb = 0; gb < groups; gb += nslots) {
+        const int g = gb + slot;
         float a = 0.0f, b = 0.0f;
-        for (int cc = 0; cc < cpg; ++cc) {
-            const float2 t = acc[threadIdx.x * cpg + cc];
-            a += t.x;
-            b += t.y;
+        if (g < groups) {
+            const int cnt = rows_per_iter * cpg;
+            for (int e = lane8; e < cnt; e += 8) {
+                const int r = e / cpg, cc = e - r * cpg;
+                const float2 t = acc[r * C + g * cpg + cc];
+                a += t.x;
+                b += t.y;
+            }
         }
-        reinterpret_cast<float2*>(partial)[(static_cast<long long>(n) * cps + blockIdx.x) * groups + threadIdx.x] =
-            make_float2(a, b);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (g < groups && lane8 == 0)
+            reinterpret_cast<float2*>(partial)[(static_cast<long long>(n) * cps + blockIdx.x) * groups + g] = make_float2(a, b);
     }
-    // per-sample barrier
-    __threadfence();
+    // per-sample barrier (thread 0 fences on behalf of the CTA: the bar.sync orders the partial stores before it)
     __syncthreads();
+    KDBG(3);
     if (threadIdx.x == 0) {
-        const unsigned gen = s_gen;
-        const unsigned prev = atomicAdd(barrier + 2 * n, 1u);
-        if (prev == static_cast<unsigned>(cps - 1)) {
-            barrier[2 * n] = 0u;
-            __threadfence();
-            st_release_u32(barrier + 2 * n + 1, gen + 1u);
-        } else {
+        __threadfence();
+        const unsigned w = blockIdx.x == 0 ? GN_BAR_QUANTUM - static_cast<unsigned>(cps - 1) : 1u;
+        const unsigned prev = atomicAdd(barrier + n, w);
+        const unsigned target = (prev / GN_BAR_QUANTUM + 1u) * GN_BAR_QUANTUM;
+        if (prev + w != target) {
             const long long t0 = clock64();
-            while (ld_acquire_u32(barrier + 2 * n + 1) == gen) {
+            while (static_cast<int>(ld_acquire_u32(barrier + n) - target) < 0) {
                 if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a CTA of this grid never became resident
             }
         }
+        __threadfence();
     }
     __syncthreads();
+    KDBG(4);
     pdl_launch_dependents();
-    // fold the partials of all CTAs of this sample: thread (slice q, group g) sums j = q, q+16, ... then slices in order
+    // fold the partials of all CTAs of this sample: eight lanes per group, lane l sums partials l, l+8, ... in order (all
+    // loads of a lane in flight together), then the same fixed butterfly
     {
-        const int g = threadIdx.x % 32, q = threadIdx.x / 32;
-        const int nq = min(16, static_cast<int>(blockDim.x / 32));
-        for (int gb = 0; gb < groups; gb += 32) {
-            if (q < nq) {
-                double a = 0.0, b = 0.0;
-                if (gb + g < groups) {
-                    const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * cps * groups + gb + g;
-                    for (int j = q; j < cps; j += nq) {
-                        const float2 t = __ldcg(pp + static_cast<long long>(j) * groups);
-                        a += static_cast<double>(t.x);
-                        b += static_cast<double>(t.y);
+        const float inv_count = 1.0f / (static_cast<float>(HW) * static_cast<float>(cpg));
+        for (int gb = 0; gb < groups; gb += nslots) {
+            const int g = gb + slot;
+            double a = 0.0, b = 0.0;
+            if (g < groups) {
+                const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * cps * groups + g;
+                for (int j = lane8; j < cps; j += 64) {
+                    float2 t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        t[u] = (j + 8 * u < cps) ? __ldcg(pp + static_cast<long long>(j + 8 * u) * groups) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        a += static_cast<double>(t[u].x);
+                        b += static_cast<double>(t[u].y);
                     }
                 }
-                s_red[q][g][0] = a;
-                s_red[q][g][1] = b;
             }
-            __syncthreads();
-            if (threadIdx.x < 32 && gb + g < groups) {
-                double a = 0.0, b = 0.0;
-                for (int r = 0; r < nq; ++r) {
-                    a += s_red[r][g][0];
-                    b += s_red[r][g][1];
-                }
-                const double count = static_cast<double>(HW) * cpg;
-                const double mean = a / count;
-                double var = b / count - mean * mean;
-                if (var < 0.0) var = 0.0;
-                s_stat[gb + g][0] = static_cast<float>(mean);
-                s_stat[gb + g][1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
             }
-            __syncthreads();
+            if (g < groups && lane8 == 0) {
+                const double mean = a * static_cast<double>(inv_count);
+                double var = b * static_cast<double>(inv_count) - mean * mean;
+                const float v = fmaxf(static_cast<float>(var), 0.0f) + eps;
+                float r = rsqrtf(v);
+                r = r * (1.5f - 0.5f * v * r * r);  // one Newton step: full fp32 accuracy
+                s_stat[g][0] = static_cast<float>(mean);
+                s_stat[g][1] = r;
+            }
         }
     }
+    __syncthreads();
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int ch = c + e;
-        const int g = ch / cpg;
-        sc[e] = s_stat[g][1] * __ldg(gamma + ch);
-        sh[e] = __ldg(beta + ch) - s_stat[g][0] * sc[e];
+        const int g = (c + e) / cpg;
+        sc[e] = s_stat[g][1] * ga[e];
+        sh[e] = be[e] - s_stat[g][0] * sc[e];
     }
+    KDBG(5);
     __half* dst = out + static_cast<long long>(n) * HW * C + c;
     for (p = p0 + prow; p < p1; p += rows_per_iter) {
         float f[8];
@@ -502,6 +532,7 @@ __global__ void __launch_bounds__(512)
         }
         st8(dst + static_cast<long long>(p) * C, pack8(f));
     }
+    KDBG(6);
 }
 
 static int gn_fused_enabled() {
@@ -539,8 +570,15 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     }
     const int cpg = C / groups;
     if (gn_fused_enabled() && CV <= 512 && Nimg <= gn_sm_count()) {
-        int rows_per_iter = 512 / CV;
-        if (rows_per_iter > HW) rows_per_iter = HW;
+        // block = CV * rows_per_iter threads, a multiple of 32 (the group reductions use full-warp shuffles)
+        int gcd = CV, t32 = 32;
+        while (t32) {
+            const int r = gcd % t32;
+            gcd = t32;
+            t32 = r;
+        }
+        const int mult = 32 / gcd;
+        int rows_per_iter = (512 / CV) / mult * mult;
         const int threads = CV * rows_per_iter;
         int cps = gn_sm_count() / Nimg;
         // keep at least ~8 KB of rows per CTA and no more CTAs than row groups
@@ -551,7 +589,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         const int rpc = (HW + cps - 1) / cps;
         cps = (HW + rpc - 1) / rpc;
         const size_t smem = static_cast<size_t>(rpc) * C * sizeof(__half) + static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
-        if (smem <= 200 * 1024 && threads >= 32 && threads >= (groups < 32 ? groups : 32) && threads >= groups) {
+        if (rows_per_iter >= 1 && smem <= 200 * 1024 && groups <= 256) {
             static bool attr_set = false;
             if (!attr_set) {
                 if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
@@ -564,7 +602,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
                 return -1;
             }
             launch_k(gn_fused_kernel, dim3(cps, Nimg), dim3(threads), smem, st, x0, C0, x1, C1, HW, groups, rpc, stats_ws, barrier,
-                     gamma, beta, eps, silu, out);
+                     gamma, beta, eps, silu, out, g_kdbg);
             return check_launch("gn_fused");
         }
     }

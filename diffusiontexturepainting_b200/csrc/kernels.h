@@ -9,6 +9,8 @@
 namespace dtp {
 
 const char* kernels_last_error();
+// debug aid: per-CTA globaltimer checkpoints (8 slots per CTA) of the single-launch GroupNorm kernel; nullptr = off
+void kernels_set_debug(long long* dbg);
 
 // GroupNorm (+SiLU) over one or two NHWC sources (channel concat, never materialised before the norm).
 // stats_ws: float[Nimg * chunks * groups * 2 + Nimg * groups * 2]
