@@ -892,13 +892,39 @@ size_t gemm_workspace_bytes(const GemmOp* op) {
     return static_cast<size_t>(p.nz1) * p.nz2 * p.splits * p.M * static_cast<size_t>(p.N) * sizeof(float);
 }
 
+// Measured configurations for the problem shapes of the benchmark workloads (profiles/make_gemm_table.py). DTP_GEMM_TABLE=0
+// falls back to the cost model everywhere.
+struct TunedCfg {
+    int mtiles, N, num_kb, geglu, BN, splits;
+};
+static const TunedCfg g_tuned[] = {
+#include "gemm_tuned.inc"
+};
+static bool tuned_lookup(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
+    static const int on = []() {
+        const char* e = getenv("DTP_GEMM_TABLE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    if (!on || (flags & (GEMM_B_MN | GEMM_W_BLOCKED | EPI_SOFTMAX16 | GEMM_HINT_CL2))) return false;
+    const int geglu = (flags & EPI_GEGLU) ? 1 : 0;
+    for (const TunedCfg& t : g_tuned)
+        if (t.mtiles == mtiles && t.N == N && t.num_kb == num_kb && t.geglu == geglu) {
+            *BN = t.BN;
+            *splits = t.splits;
+            return true;
+        }
+    return false;
+}
+
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
+    if (tuned_lookup(mtiles, N, num_kb, flags, BN, splits)) return;
     // Cost model (SM cycles) of the persistent kernel, searched over (BN, split-K):
     //   per k-block the tensor pipe needs 2*BN cycles (128 x BN x 64 MACs at 4096 MAC/clk/SM) and the TMA feed
     //   (16 KB of A + 128*BN B of B) moves ~64 B/clk per SM (measured); chip-wide the L2 -> SM fabric sustains
     //   ~7000 B/clk (measured ~14 TB/s on an 8192^3 problem), which bounds kernels whose tiles re-read A / B many times;
-    //   the epilogue of a tile (~350 clk per 32 columns) overlaps the next tile's mainloop;
-    //   split-K adds an fp32 partial write + a finalize pass (launch ~2000 clk + bytes at ~2500 B/clk).
+    //   the epilogue of a tile (~510 clk per 32 columns) overlaps the next tile's mainloop;
+    //   split-K adds an fp32 partial write + a finalize pass (launch ~4900 clk + bytes at ~4200 B/clk).
+    // Constants fitted to the CUDA-graph-timed sweep in profiles/gemm_sweep_r1.csv (regret 2.2 % over its 62 shapes).
     const int kSMs = 148;
     static const int cand_k[] = {32, 64, 128, 160, 192, 256};
     static const int cand_mn[] = {64, 128, 192, 256};
@@ -913,24 +939,24 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
         if (bn >= 64 && bn - 32 >= ((N + 31) / 32) * 32) continue;  // mostly padding
         const long long gn = (N + bn - 1) / bn;
         const double t_mma = 2.0 * bn;
-        const double t_tma = (16384.0 + ((flags & GEMM_HINT_CL2) ? 64.0 : 128.0) * bn) / 58.0;
+        const double t_tma = (16384.0 + ((flags & GEMM_HINT_CL2) ? 64.0 : 128.0) * bn) / 61.0;
         const double t_kb = t_mma > t_tma ? t_mma : t_tma;
-        const double t_epi = 300.0 + (bn / 32) * 350.0;
+        const double t_epi = (bn / 32) * 510.0;
         const int max_sp = (flags & GEMM_B_MN) ? 1 : 16;
         for (int sp = 1; sp <= max_sp; ++sp) {
             if (sp > 1 && num_kb / sp < 4) break;
             const long long tiles = static_cast<long long>(mtiles) * gn * sp;
             const double kb_per = static_cast<double>(num_kb) / sp;
             const double t_main = kb_per * t_kb;
-            const double t_epi_eff = sp > 1 ? 400.0 : t_epi;
-            const double t_tile = (t_main > t_epi_eff ? t_main : t_epi_eff) + 200.0;
+            const double t_epi_eff = sp > 1 ? 1800.0 : t_epi;
+            const double t_tile = (t_main > t_epi_eff ? t_main : t_epi_eff) + 800.0;
             const double per_cta = static_cast<double>((tiles + kSMs - 1) / kSMs);
-            double cost = per_cta * t_tile + t_epi_eff + 1500.0;
+            double cost = per_cta * t_tile + t_epi_eff + 7900.0;
             const double l2_bytes = static_cast<double>(mtiles) * gn * num_kb *
                                     (16384.0 + ((flags & GEMM_HINT_CL2) ? 64.0 : 128.0) * bn);
             const double t_l2 = l2_bytes / 7000.0;
             if (t_l2 > cost) cost = t_l2;
-            if (sp > 1) cost += 2000.0 + rows * N * 4.0 * (sp + 1) / 2500.0;
+            if (sp > 1) cost += 4900.0 + rows * N * 4.0 * (sp + 1) / 4200.0;
             if (best_cost < 0 || cost < best_cost * 0.97 || (cost <= best_cost && bn > best && sp <= best_sp)) {
                 best_cost = cost;
                 best = bn;

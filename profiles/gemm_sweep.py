@@ -14,78 +14,123 @@ L = nat.lib()
 dev = "cuda"
 
 
-def timeit(fn, reps=10):
-    for _ in range(2):
-        fn()
+def timeit(mk_call, nbuf):
+    """Device-bound time per launch: `reps` launches (cycling through nbuf weight buffers so weights stay cold, as in a
+    stamp where 1.7 GB of weights stream per UNet evaluation) captured into one CUDA graph and replayed 3 times."""
+    reps = max(nbuf, 12)
+    for i in range(nbuf):
+        mk_call(i)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        fn()
-    e1.record()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(reps):
+                mk_call(i)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(3):
+            graph.replay()
+        e1.record(side)
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / reps
+    return e0.elapsed_time(e1) * 1e3 / (3 * reps)
+
+
+def ring(nbytes):
+    return max(1, min(24, int(300e6 // nbytes)))
 
 
 def sweep_linear(M, N, K, flags=0):
+    nbuf = ring(N * K * 2)
     A = torch.randn(M, K, device=dev).half()
-    W = torch.randn(N, K, device=dev).half()
+    Ws = [torch.randn(N, K, device=dev).half() for _ in range(nbuf)]
     out = torch.empty(M, N // 2 if flags & 8 else N, device=dev, dtype=torch.float16)
     bias = torch.randn(N, device=dev)
     res = {}
 
     def mk(BN, sp):
-        def f():
-            nat.check_op(L.dtp_op_linear(nat.ptr(A), K, K, None, 0, 0, M, nat.ptr(W), K, N, nat.ptr(bias), None, 0,
+        def f(i):
+            nat.check_op(L.dtp_op_linear(nat.ptr(A), K, K, None, 0, 0, M, nat.ptr(Ws[i % nbuf]), K, N, nat.ptr(bias), None, 0,
                                          nat.ptr(out), out.shape[1], flags, 1.0, 0, BN, sp, nat.stream_ptr()))
         return f
     for BN in (32, 64, 128, 160, 192, 256):
-        for sp in (1, 2, 3, 4, 6, 8, 12):
+        if BN > 64 and BN - 32 >= N:
+            continue
+        for sp in (1, 2, 3, 4, 6, 8, 12, 16):
             if sp > 1 and (K // 64) // sp < 2:
                 continue
-            res[(BN, sp)] = timeit(mk(BN, sp))
-    auto = timeit(mk(0, 1))
+            res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
+    auto = timeit(mk(0, 1), nbuf)
     report(f"linear M={M} N={N} K={K} flags={flags}", res, auto, 2.0 * M * N * K)
 
 
 def sweep_conv(n, H, Wd, cin, cout):
+    nbuf = ring(cout * 9 * cin * 2)
     x = torch.randn(n, H, Wd, cin, device=dev).half()
-    w = torch.randn(cout, 9 * cin, device=dev).half()
+    ws = [torch.randn(cout, 9 * cin, device=dev).half() for _ in range(nbuf)]
     out = torch.empty(n, H, Wd, cout, device=dev, dtype=torch.float16)
     bias = torch.randn(cout, device=dev)
     res = {}
 
     def mk(BN, sp):
-        def f():
-            nat.check_op(L.dtp_op_conv3x3(nat.ptr(x), cin, None, 0, n, H, Wd, nat.ptr(w), cout, nat.ptr(bias), None, 0,
+        def f(i):
+            nat.check_op(L.dtp_op_conv3x3(nat.ptr(x), cin, None, 0, n, H, Wd, nat.ptr(ws[i % nbuf]), cout, nat.ptr(bias), None, 0,
                                           nat.ptr(out), cout, 0, 1.0, 0, BN, sp, nat.stream_ptr()))
         return f
     for BN in (32, 64, 128, 160, 192, 256):
         if BN > 64 and BN - 32 >= cout:
             continue
         for sp in (1, 2, 3, 4, 6, 8, 12, 16):
-            res[(BN, sp)] = timeit(mk(BN, sp))
-    auto = timeit(mk(0, 1))
+            if sp > 1 and (9 * cin // 64) // sp < 2:
+                continue
+            res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
+    auto = timeit(mk(0, 1), nbuf)
     report(f"conv3x3 n={n} {H}x{Wd} cin={cin} cout={cout} (M={n*H*Wd} K={9*cin})", res, auto,
            2.0 * n * H * Wd * cout * 9 * cin)
 
 
+CSV = open(os.path.join(ROOT, "gpurun_out", "sweep_all.csv"), "a") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
+
+
 def report(name, res, auto, flops):
-    best = sorted(res.items(), key=lambda kv: kv[1])[:4]
+    if CSV:
+        for (bn, sp), v in sorted(res.items()):
+            CSV.write(f"{name};{bn};{sp};{v:.2f}\n")
+        CSV.write(f"{name};0;0;{auto:.2f}\n")
+        CSV.flush()
+    best = sorted(res.items(), key=lambda kv: kv[1])[:5]
     s = ", ".join(f"BN={k[0]} sp={k[1]}: {v:.1f}us" for k, v in best)
     print(f"{name}: auto {auto:.1f}us ({flops / auto / 1e6:.0f} TF) | best {s} ({flops / best[0][1] / 1e6:.0f} TF)",
           flush=True)
 
 
 if __name__ == "__main__":
-    for shp in [(12288, 320, 320), (12288, 960, 320), (12288, 320, 1280), (3072, 640, 640), (3072, 1920, 640),
-                (3072, 640, 2560), (768, 1280, 1280), (768, 3840, 1280), (768, 1280, 5120), (192, 1280, 1280),
-                (192, 1280, 5120), (192, 3840, 1280)]:
-        sweep_linear(*shp)
-    for shp in [(12288, 2560, 320), (3072, 5120, 640), (768, 10240, 1280), (192, 10240, 1280)]:
-        sweep_linear(*shp, flags=8)
-    for shp in [(3, 64, 64, 320, 320), (3, 64, 64, 640, 320), (3, 64, 64, 960, 320), (3, 32, 32, 640, 640),
-                (3, 32, 32, 1280, 640), (3, 32, 32, 1920, 640), (3, 16, 16, 1280, 1280), (3, 16, 16, 2560, 1280),
-                (3, 8, 8, 1280, 1280), (3, 8, 8, 2560, 1280), (2, 512, 512, 128, 128), (2, 256, 256, 256, 256),
-                (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:
-        sweep_conv(*shp)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "linear"):
+        for shp in [(12288, 320, 320), (12288, 960, 320), (12288, 320, 1280), (12288, 320, 640), (3072, 640, 640),
+                    (3072, 1920, 640), (3072, 640, 2560), (3072, 640, 1280), (3072, 320, 2880), (768, 1280, 1280),
+                    (768, 3840, 1280), (768, 1280, 5120), (768, 1280, 2560), (768, 640, 5760), (192, 1280, 1280),
+                    (192, 1280, 2560), (192, 1280, 5120), (192, 1280, 11520), (192, 3840, 1280)]:
+            sweep_linear(*shp)
+        for shp in [(12288, 2560, 320), (3072, 5120, 640), (768, 10240, 1280), (192, 10240, 1280)]:
+            sweep_linear(*shp, flags=8)
+    if which in ("all", "conv"):
+        for shp in [(3, 64, 64, 320, 320), (3, 64, 64, 640, 320), (3, 64, 64, 960, 320), (3, 64, 64, 640, 640),
+                    (3, 32, 32, 320, 640), (3, 32, 32, 640, 640), (3, 32, 32, 960, 640), (3, 32, 32, 1280, 640),
+                    (3, 32, 32, 1920, 640), (3, 32, 32, 1280, 1280), (3, 16, 16, 640, 1280), (3, 16, 16, 1280, 1280),
+                    (3, 16, 16, 1920, 1280), (3, 16, 16, 2560, 1280), (3, 8, 8, 1280, 1280), (3, 8, 8, 2560, 1280)]:
+            sweep_conv(*shp)
+    if which in ("all", "r256"):
+        for shp in [(3072, 320, 320), (3072, 960, 320), (3072, 320, 1280), (768, 640, 640), (768, 1920, 640),
+                    (768, 640, 2560), (48, 1280, 1280), (48, 1280, 5120)]:
+            sweep_linear(*shp)
+        for shp in [(3072, 2560, 320), (768, 5120, 640), (48, 10240, 1280)]:
+            sweep_linear(*shp, flags=8)
+        for shp in [(3, 32, 32, 320, 320), (3, 32, 32, 640, 320), (3, 32, 32, 960, 320), (3, 16, 16, 640, 640),
+                    (3, 16, 16, 1280, 640), (3, 16, 16, 960, 640), (3, 4, 4, 1280, 1280), (3, 4, 4, 2560, 1280)]:
+            sweep_conv(*shp)
+    if which in ("all", "vae"):
+        for shp in [(2, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:
+            sweep_conv(*shp)
