@@ -82,6 +82,17 @@ __device__ __forceinline__ void tma_load_4d_mc(void* smem, const CUtensorMap* m,
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
         : "memory");
 }
+// CTA-pair variant: issued by BOTH CTAs of a cta_group::2 pair; the box lands in the issuing CTA's shared memory, the
+// transaction bytes are counted on the mbarrier at the same offset in the LEADER (even-rank) CTA: bit 24 of a shared::cluster
+// address selects the CTA of the pair, clearing it addresses the leader.
+__device__ __forceinline__ void tma_load_4d_pair(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2];" ::"r"(smem_u32(smem)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

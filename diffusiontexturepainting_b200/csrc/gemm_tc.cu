@@ -227,6 +227,15 @@ __device__ __forceinline__ long long gtime() {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// operand box load: in pair mode (CL == 2) the bytes are counted on the leader CTA's barrier
+template <int CL>
+__device__ __forceinline__ void tma4(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    if (CL == 2)
+        tma_load_4d_pair(smem, m, bar, c0, c1, c2, c3);
+    else
+        tma_load_4d(smem, m, bar, c0, c1, c2, c3);
+}
+
 struct TileCoord {
     int m_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
 };
@@ -341,10 +350,11 @@ __global__ void __launch_bounds__(320, OCC)
                 const TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
                 pre = min(STAGES, c0.kb_end - c0.kb_begin);
                 for (int s = 0; s < pre; ++s) {
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
+                    // pair mode: the leader's barrier counts the operand bytes of both CTAs
+                    if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[s], CL * (a_bytes + b_bytes));
                     uint8_t* sbp = smem + s * STAGE_BYTES + A_BYTES;
                     if (CL == 2)
-                        tma_load_4d(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0 + rank * BH, 0, 0);
+                        tma_load_4d_pair(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0 + rank * BH, 0, 0);
                     else if (w_blocked)
                         tma_load_4d(sbp, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
                     else
@@ -362,27 +372,27 @@ __global__ void __launch_bounds__(320, OCC)
                     uint8_t* sb = sa + A_BYTES;
                     if (!prefetched) {
                         mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+                        if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CL * (a_bytes + b_bytes));
                     }
                     if (p.mode == 1) {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
                         const int ky = tap / 3, kx = tap - ky * 3;
                         if (cb < p.cblocks0)
-                            tma_load_4d(sa, &mapA0, &full_bar[stage], cb * 64, c.x0 + kx - 1, c.y0 + ky - 1, c.img0);
+                            tma4<CL>(sa, &mapA0, &full_bar[stage], cb * 64, c.x0 + kx - 1, c.y0 + ky - 1, c.img0);
                         else
-                            tma_load_4d(sa, &mapA1, &full_bar[stage], (cb - p.cblocks0) * 64, c.x0 + kx - 1,
-                                        c.y0 + ky - 1, c.img0);
+                            tma4<CL>(sa, &mapA1, &full_bar[stage], (cb - p.cblocks0) * 64, c.x0 + kx - 1, c.y0 + ky - 1,
+                                     c.img0);
                     } else {
                         if (kb < p.cblocks0)
-                            tma_load_4d(sa, &mapA0, &full_bar[stage], kb * 64, c.m_tile * 128, za, za2);
+                            tma4<CL>(sa, &mapA0, &full_bar[stage], kb * 64, c.m_tile * 128, za, za2);
                         else
-                            tma_load_4d(sa, &mapA1, &full_bar[stage], (kb - p.cblocks0) * 64, c.m_tile * 128, za, za2);
+                            tma4<CL>(sa, &mapA1, &full_bar[stage], (kb - p.cblocks0) * 64, c.m_tile * 128, za, za2);
                     }
                     if (prefetched) {
                         // B tile of this stage is already in flight
                     } else if (CL == 2) {
-                        tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0);
+                        tma_load_4d_pair(sb, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0);
                     } else if (w_blocked) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
@@ -400,22 +410,8 @@ __global__ void __launch_bounds__(320, OCC)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && CL == 2 && rank == 1) {
-            // ------------------------------ peer CTA: forward "my operands have landed" to the leader ----------------
-            pdl_wait();
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = tile0; t < total_tiles; t += tstep) {
-                const TileCoord c = decode_tile<BN, CL>(p, t, rank);
-                for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
-                    mbar_wait_bounded(&full_bar[stage], phase);
-                    mbar_arrive_remote(&peer_full_bar[stage], 0);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
+        if (CL == 2 && rank == 1) {
+            // peer CTA of a pair: its operands are consumed by the leader's MMAs (its TMA loads report to the leader's barriers)
         } else if (lane == 0) {
             // ------------------------------ MMA issuer (leader CTA in pair mode) ------------------------------
             const uint32_t idesc = umma_idesc_f16(128 * CL, BN, 0, b_mn ? 1 : 0);
@@ -432,7 +428,6 @@ __global__ void __launch_bounds__(320, OCC)
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
                     mbar_wait_bounded(&full_bar[stage], phase);
-                    if (CL == 2) mbar_wait_bounded(&peer_full_bar[stage], phase);
                     if (first) {
                         DBG_MARK(2);
                         first = false;
