@@ -333,6 +333,11 @@ __device__ __forceinline__ void ld_global_nc_v8(const void* ptr, uint32_t (&r)[8
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "l"(ptr));
 }
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
 __device__ __forceinline__ bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31) == 0; }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);

@@ -437,21 +437,29 @@ __global__ void __launch_bounds__(384, 1)
                 kph ^= 1;
             }
             for (int j = 0; j < nblk; ++j) {
-                const bool more = j + 1 < nblk;
+                // The scores of block j + 1 only need the S columns back (s_empty: the softmax warps hold block j in
+                // registers), not P_j: issue them FIRST, so they are ready long before the warpgroup finishes its
+                // exponentials, and only then the two P V products of block j.
+                if (j + 1 < nblk) {
+                    fa_wait(&k_full[kst], kph);
+                    const uint32_t k_addr = smem_u32(sK + kst * TILE_BYTES);
+                    fa_wait(&s_empty[0], j & 1);
+                    tc_fence_after();
+                    issue_s(0, k_addr);
+                    fa_wait(&s_empty[1], j & 1);
+                    tc_fence_after();
+                    issue_s(1, k_addr);
+                    umma_commit(&k_empty[kst]);
+                    if (++kst == KS) {
+                        kst = 0;
+                        kph ^= 1;
+                    }
+                }
                 fa_wait(&v_full[vst], vph);
                 const uint32_t v_addr = smem_u32(sV + vst * TILE_BYTES);
-                uint32_t k_addr = 0;
-                // query tile 0: O0 += P0_j V_j, then its next scores as soon as K_{j+1} has landed
                 fa_wait(&p_full[0], j & 1);
                 tc_fence_after();
                 issue_pv(0, v_addr, j);
-                if (more) {
-                    fa_wait(&k_full[kst], kph);
-                    tc_fence_after();
-                    k_addr = smem_u32(sK + kst * TILE_BYTES);
-                    issue_s(0, k_addr);  // s_empty[0] of block j was signalled before p_full[0]
-                }
-                // query tile 1
                 fa_wait(&p_full[1], j & 1);
                 tc_fence_after();
                 issue_pv(1, v_addr, j);
@@ -459,14 +467,6 @@ __global__ void __launch_bounds__(384, 1)
                 if (++vst == KS) {
                     vst = 0;
                     vph ^= 1;
-                }
-                if (more) {
-                    issue_s(1, k_addr);
-                    umma_commit(&k_empty[kst]);
-                    if (++kst == KS) {
-                        kst = 0;
-                        kph ^= 1;
-                    }
                 }
             }
         }
@@ -515,8 +515,6 @@ __global__ void __launch_bounds__(384, 1)
                 }
             }
             bm *= sc;
-            if (j > 0) fa_wait(&o_done[w], (j - 1) & 1);
-            tc_fence_after();
             bool need = false;
             float factor = 1.0f;
             if (j == 0) {
@@ -526,6 +524,25 @@ __global__ void __launch_bounds__(384, 1)
                 factor = ex2_approx(m_used - bm);
                 m_used = bm;
             }
+            // exponentials first, packed to fp16 in registers: they depend on neither O nor the P buffer, so the latency of
+            // the previous block's P V product (o_done) hides behind the MUFU work instead of stalling the warp in front of it
+            const float neg_m = -m_used;
+            float l0 = 0.0f, l1 = 0.0f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int c = 0; c < 128; c += 8) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
+                l0 += (e[0] + e[1]) + (e[2] + e[3]);
+                l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                pk[(c >> 1) + 0] = pack_half2(e[0], e[1]);
+                pk[(c >> 1) + 1] = pack_half2(e[2], e[3]);
+                pk[(c >> 1) + 2] = pack_half2(e[4], e[5]);
+                pk[(c >> 1) + 3] = pack_half2(e[6], e[7]);
+            }
+            if (j > 0) fa_wait(&o_done[w], (j - 1) & 1);  // P buffer free again, O_{j-1} final
+            tc_fence_after();
             if (__any_sync(0xffffffffu, need)) {
                 l *= factor;
                 for (int c = 0; c < p.dN; c += 32) {
@@ -538,25 +555,11 @@ __global__ void __launch_bounds__(384, 1)
                 }
                 tmem_st_wait();
             }
-            const float neg_m = -m_used;
-            float l0 = 0.0f, l1 = 0.0f;
-#pragma unroll
-            for (int c = 0; c < 128; c += 8) {
-                float e[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
-                l0 += (e[0] + e[1]) + (e[2] + e[3]);
-                l1 += (e[4] + e[5]) + (e[6] + e[7]);
-                __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
-                __half2 h2 = __floats2half2_rn(e[4], e[5]), h3 = __floats2half2_rn(e[6], e[7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0);
-                u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2);
-                u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(prow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) = u;
-            }
             l += l0 + l1;
+#pragma unroll
+            for (int c = 0; c < 128; c += 8)
+                *reinterpret_cast<uint4*>(prow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) =
+                    make_uint4(pk[(c >> 1) + 0], pk[(c >> 1) + 1], pk[(c >> 1) + 2], pk[(c >> 1) + 3]);
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();

@@ -237,7 +237,7 @@ __device__ __forceinline__ void tma4(void* smem, const CUtensorMap* m, uint64_t*
 }
 
 struct TileCoord {
-    int m_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
+    int m_tile, n_tile, n0, z1, z2, zsplit, zb, kb_begin, kb_end, x0, y0, img0;
 };
 // CL = 2: `t` indexes a PAIR of adjacent m-tiles handled by the two CTAs of a cluster (same n-tile, same k-range)
 template <int BN, int CL>
@@ -253,6 +253,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
     c.z1 = c.zb % p.nz1;
     c.z2 = c.zb / p.nz1;
     c.n0 = n_tile * BN;
+    c.n_tile = n_tile;
     c.kb_begin = static_cast<int>(static_cast<long long>(c.zsplit) * p.num_kb / p.splits);
     c.kb_end = static_cast<int>(static_cast<long long>(c.zsplit + 1) * p.num_kb / p.splits);
     c.x0 = c.y0 = c.img0 = 0;
@@ -265,6 +266,23 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
         c.img0 = tn * p.bn;
     }
     return c;
+}
+
+__device__ __forceinline__ int tile_group(const GemmParams& p, const TileCoord& c) {
+    return (c.zb * p.grid_n + c.n_tile) * p.grid_m + c.m_tile;
+}
+// output row (NHWC pixel index / matrix row) of tile-local row r, or -1 when r is padding
+__device__ __forceinline__ int tile_row(const GemmParams& p, const TileCoord& c, int r) {
+    if (p.mode == 1) {
+        if (r >= p.rows_valid) return -1;
+        const int w = r % p.bw;
+        const int hh = (r / p.bw) % p.bh;
+        const int nn = r / (p.bw * p.bh);
+        const int img = c.img0 + nn;
+        return (img < p.Nimg) ? (img * p.H + c.y0 + hh) * p.W + c.x0 + w : -1;
+    }
+    const int m = c.m_tile * 128 + r;
+    return (m < p.M) ? m : -1;
 }
 
 // Persistent kernel: grid = min(tiles, SMs); every role walks the same static tile sequence t = blockIdx.x + i*gridDim.x.
@@ -293,6 +311,7 @@ __global__ void __launch_bounds__(320, OCC)
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint64_t* peer_full_bar = tmem_empty_bar + 2;   // [STAGES] leader only: the peer CTA's operands of a stage have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full_bar + STAGES);
+    int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);  // split-K arrival ticket of the current tile (epilogue warps)
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
 
     const int warp = threadIdx.x >> 5;
@@ -477,22 +496,11 @@ __global__ void __launch_bounds__(320, OCC)
         pdl_wait();
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0 && p.splits == 1;
+        const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
+        const bool fused_reduce = p.splits > 1 && p.tile_counters != nullptr;
         for (int t = tile0; t < total_tiles; t += tstep) {
             const TileCoord c = decode_tile<BN, CL>(p, t, rank);
-            int row = -1;
-            if (p.mode == 1) {
-                if (r < p.rows_valid) {
-                    const int w = r % p.bw;
-                    const int hh = (r / p.bw) % p.bh;
-                    const int nn = r / (p.bw * p.bh);
-                    const int img = c.img0 + nn;
-                    if (img < p.Nimg) row = (img * p.H + c.y0 + hh) * p.W + c.x0 + w;
-                }
-            } else {
-                const int m = c.m_tile * 128 + r;
-                if (m < p.M) row = m;
-            }
+            const int row = tile_row(p, c, r);
             const long long out_off = static_cast<long long>(c.z1) * p.out_zs1 + static_cast<long long>(c.z2) * p.out_zs2;
             const long long res_off = static_cast<long long>(c.z1) * p.res_zs1 + static_cast<long long>(c.z2) * p.res_zs2;
             if (col_bias) {
@@ -539,7 +547,15 @@ __global__ void __launch_bounds__(320, OCC)
                             mbar_arrive(&tmem_empty_bar[acc]);
                     }
                 }
-                if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
+                if (fused_reduce) {
+                    // tile-contiguous partial [group][split][128 rows][BN]: every row of the tile is written (padding rows too)
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                    float* ws = p.workspace +
+                                ((static_cast<long long>(tile_group(p, c)) * p.splits + c.zsplit) * 128 + r) * BN + cc;
+                    store_f32_chunk(ws, v, 32, true);
+                } else if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
@@ -553,6 +569,75 @@ __global__ void __launch_bounds__(320, OCC)
                     } else {
                         epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
                     }
+                }
+            }
+            if (fused_reduce) {
+                // Split-K without a second launch (host guarantees one tile per CTA and a fully co-resident grid, so waiting
+                // for the other CTAs of the split group cannot deadlock): every CTA publishes its fp32 partial, waits until
+                // the group's `splits` partials are visible, then reduces ITS row slice of the tile in split order
+                // (bit-reproducible) and runs the epilogue for that slice.
+                int* cnt = p.tile_counters + 2 * tile_group(p, c);
+                __threadfence();
+                epi_bar_sync();
+                if (et == 0) {
+                    atomicAdd(cnt, 1);
+                    const long long t0 = clock64();
+                    while (ld_acquire_gpu(cnt) < p.splits) {
+                        if (clock64() - t0 > 8000000000LL) __trap();
+                    }
+                }
+                epi_bar_sync();
+                __threadfence();
+                const int r0 = (c.zsplit * 128) / p.splits, r1 = ((c.zsplit + 1) * 128) / p.splits;
+                const float* wsg = p.workspace + static_cast<long long>(tile_group(p, c)) * p.splits * 128 * BN;
+                float* ssum = reinterpret_cast<float*>(smem);  // operand stages are idle: this CTA has no further tile
+                constexpr int P4 = BN / 4;                     // 16-byte pieces per tile row
+                for (int i = et; i < (r1 - r0) * P4; i += 256) {
+                    const int rl = i / P4, c4 = i - rl * P4;
+                    const float* src = wsg + static_cast<long long>(r0 + rl) * BN + c4 * 4;
+                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int s0 = 0; s0 < p.splits; s0 += 8) {
+                        float4 t4[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (s0 + j < p.splits)
+                                t4[j] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s0 + j) * 128 * BN));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (s0 + j < p.splits) {
+                                a4.x += t4[j].x;
+                                a4.y += t4[j].y;
+                                a4.z += t4[j].z;
+                                a4.w += t4[j].w;
+                            }
+                    }
+                    // unit u = (row, 32-column chunk) occupies 128 B; its 16-B pieces are XOR-swizzled by the unit index
+                    const int u = rl * (BN / 32) + (c4 >> 3);
+                    *reinterpret_cast<float4*>(ssum + u * 32 + (((c4 & 7) ^ (u & 7)) << 2)) = a4;
+                }
+                epi_bar_sync();
+                if (et == 0) {
+                    // all CTAs of the group have passed their wait before the last one gets here: safe to clear both slots
+                    if (atomicAdd(cnt + 1, 1) == p.splits - 1) {
+                        cnt[0] = 0;
+                        cnt[1] = 0;
+                    }
+                }
+                for (int u = et; u < (r1 - r0) * (BN / 32); u += 256) {
+                    const int rl = u / (BN / 32), ch = u - rl * (BN / 32);
+                    const int orow = tile_row(p, c, r0 + rl);
+                    const int col0 = c.n0 + ch * 32;
+                    if (orow < 0 || col0 >= p.N) continue;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(ssum + u * 32 + ((j ^ (u & 7)) << 2));
+                        v[4 * j] = t4.x;
+                        v[4 * j + 1] = t4.y;
+                        v[4 * j + 2] = t4.z;
+                        v[4 * j + 3] = t4.w;
+                    }
+                    epilogue_store32(p, out_off, res_off, orow, col0, v, col_bias ? sbias + ch * 32 : nullptr);
                 }
             }
             if (++acc == 2) {
@@ -738,6 +823,7 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
     p.cblocks0 = kb0;
     p.cblocks = kb0 + kb1;
     p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+    if (p.splits > 1) gemm_prepare_splitk();
     p.ldc = N;
     op->BN = BN;
     op->grid_m = (M + 127) / 128;
@@ -801,6 +887,7 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     p.cblocks = C / 64;
     p.num_kb = 9 * p.cblocks;
     p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+    if (p.splits > 1) gemm_prepare_splitk();
     p.ldc = Cout;
     op->BN = BN;
     op->grid_m = p.tiles_x * p.tiles_y * ((Nimg + p.bn - 1) / p.bn);
@@ -884,7 +971,12 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
 size_t gemm_workspace_bytes(const GemmOp* op) {
     const GemmParams& p = op->p;
     if (p.splits <= 1) return 0;
-    return static_cast<size_t>(p.nz1) * p.nz2 * p.splits * p.M * static_cast<size_t>(p.N) * sizeof(float);
+    // the larger of the two partial layouts: row-major [batch*splits][M][N] (separate finalize kernel) and tile-contiguous
+    // [tile group][split][128][BN] (in-kernel reduction)
+    const size_t flat = static_cast<size_t>(p.nz1) * p.nz2 * p.splits * p.M * static_cast<size_t>(p.N);
+    const size_t tiled = static_cast<size_t>(p.nz1) * p.nz2 * p.splits * op->grid_m * ((p.N + op->BN - 1) / op->BN) * 128 *
+                         static_cast<size_t>(op->BN);
+    return (flat > tiled ? flat : tiled) * sizeof(float);
 }
 
 // Measured configurations for the problem shapes of the benchmark workloads (profiles/make_gemm_table.py). DTP_GEMM_TABLE=0
@@ -963,6 +1055,50 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
     *splits = best_sp;
 }
 
+// Arrival tickets of the fused split-K reduction: zeroed once, self-resetting afterwards (the last arriver of a tile clears
+// its slot), shared by all launches of a stream. Allocated from the setup functions, i.e. never during graph capture.
+static const int kTileCounterSlots = 1 << 16;
+static int* g_tile_counters = nullptr;
+static int* tile_counters() {
+    static const int on = []() {
+        const char* e = getenv("DTP_SPLITK_FUSED");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    if (!on) return nullptr;
+    if (g_tile_counters == nullptr) {
+        int* ptr = nullptr;
+        if (cudaMalloc(&ptr, kTileCounterSlots * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        if (cudaMemset(ptr, 0, kTileCounterSlots * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(ptr);
+            return nullptr;
+        }
+        g_tile_counters = ptr;
+    }
+    return g_tile_counters;
+}
+void gemm_prepare_splitk() { (void)tile_counters(); }
+static int num_sms();
+static int max_pair_clusters();
+// The in-kernel split-K reduction waits for the other CTAs of a tile's split group, so it is only used when every CTA owns
+// exactly one tile and the whole grid is co-resident (tiles <= SMs; CTA pairs: <= the co-resident cluster count).
+static bool splitk_fused(const GemmOp* op) {
+    const GemmParams& p = op->p;
+    if (p.splits <= 1 || g_tile_counters == nullptr) return false;
+    const long long gn = (p.N + op->BN - 1) / op->BN;
+    const long long groups = static_cast<long long>(op->grid_m) * gn * p.nz1 * p.nz2;
+    if (2 * groups > kTileCounterSlots) return false;
+    if (op->cluster == 2) {
+        const long long pair_tiles = static_cast<long long>((op->grid_m + 1) / 2) * gn * p.nz1 * p.nz2 * p.splits;
+        return pair_tiles <= max_pair_clusters();
+    }
+    return groups * p.splits <= num_sms();
+}
+int gemm_num_launches(const GemmOp* op) { return (op->p.splits > 1 && !splitk_fused(op)) ? 2 : 1; }
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -997,6 +1133,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     const int cap = 2 * num_sms();
+    p.tile_counters = (tiles <= cap && splitk_fused(op)) ? g_tile_counters : nullptr;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
     cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1040,9 +1177,10 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         return -24;
     }
     p.total_tiles = static_cast<int>(tiles);
+    p.tile_counters = splitk_fused(op) ? g_tile_counters : nullptr;
     cudaError_t e;
     if (cl == 2) {
-        const int max_clusters = num_sms() / 2;
+        const int max_clusters = num_sms() / 2;  // (fused split-K additionally requires tiles <= max_pair_clusters())
         const int nclusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * nclusters);
@@ -1070,6 +1208,33 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         return -21;
     }
     return 0;
+}
+
+// co-resident 2-CTA clusters of the pair-mode kernel (one CTA per SM for every instantiation; queried on one of them)
+static int max_pair_clusters() {
+    static int n = -1;
+    if (n < 0) {
+        constexpr int SMEM2 = 8 * (128 * 128 + 128 * 64) + (3 * 8 + 4) * 8 + 16 + 128 * 4 + 1024;
+        cudaFuncSetAttribute(gemm_tc_kernel<128, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (num_sms() / 2));
+        cfg.blockDim = dim3(320);
+        cfg.dynamicSmemBytes = SMEM2;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int c = 0;
+        if (cudaOccupancyMaxActiveClusters(&c, gemm_tc_kernel<128, 8, 2>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            c = 0;
+        }
+        n = c;
+    }
+    return n;
 }
 
 int gemm_launch(const GemmOp* op, cudaStream_t stream) {
@@ -1104,7 +1269,7 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
         default: r = launch_cfg<256, 4, 6>(op, stream); break;
     }
     if (r) return r;
-    if (p.splits > 1) {
+    if (p.splits > 1 && !splitk_fused(op)) {
         const int chunks = (p.N + 31) / 32;
         const long long total = static_cast<long long>(p.nz1) * p.nz2 * p.M * chunks;
         const int blocks = static_cast<int>((total + 255) / 256);

@@ -46,7 +46,8 @@ struct GemmParams {
     int rows_valid;    // conv: bw*bh*bn (<= 128) rows of the tile that map to pixels
     int cblocks0;      // 64-channel blocks (per tap) that come from source 0
     int cblocks;       // 64-channel blocks per tap (source 0 + source 1); linear: == num_kb
-    int splits;        // split-K factor; > 1 writes fp32 partials to workspace and a finalize kernel runs the epilogue
+    int splits;        // split-K factor; > 1 writes fp32 partials to workspace; the last-arriving CTA of a tile sums them and
+                       // runs the epilogue (tile_counters), or a finalize kernel does (tile_counters == nullptr)
     int nz1, nz2;      // batch extents (heads, samples); grid.z = nz1 * nz2 * splits
     int a_batched;     // A map uses (z1,z2) as coords 2,3
     int b_batched;     // B map uses (z1,z2) as coords 2,3
@@ -62,6 +63,7 @@ struct GemmParams {
     const __half* residual;   // [M, ldr] fp16, nullable
     void* out;                // fp16 [M, ldc] (default) / fp32 variants
     float* workspace;         // [batch*splits, Mpad, N] fp32
+    int* tile_counters;       // split-K arrival tickets, one per (batch, n-tile, m-tile); nullptr -> separate finalize launch
     long long* dbg;           // optional: per-CTA globaltimer checkpoints [ctas][8] (tuning aid), nullable
     int grid_m, grid_n, total_tiles;  // filled at launch: tile grid of the persistent scheduler
     int dbg_mode;      // tuning aid (DTP_EPI_DEBUG): 1 = skip global stores, 2 = skip TMEM loads
@@ -96,6 +98,10 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
                        long long b_zs1, long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, int BN);
 
 int gemm_launch(const GemmOp* op, cudaStream_t stream);
+// kernels gemm_launch enqueues for this op: 1, or 2 when a split-K problem needs the separate finalize kernel
+int gemm_num_launches(const GemmOp* op);
+// allocates the split-K arrival tickets (called by the setup functions; never during graph capture)
+void gemm_prepare_splitk();
 size_t gemm_workspace_bytes(const GemmOp* op);
 // heuristic tile / split selection for a problem with `mtiles` 128-row tiles
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits);

@@ -215,7 +215,7 @@ struct Builder {
                 eng->err_ = std::string("contraction launch failed: ") + gemm_last_error();
                 return -1;
             }
-            return op.p.splits > 1 ? 2 : 1;
+            return gemm_num_launches(&op);
         }, label);
     }
 
