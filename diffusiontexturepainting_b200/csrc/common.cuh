@@ -72,6 +72,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* m, ui
         : "memory");
 }
 
+// 1-D bulk copy global -> shared (16-byte aligned, size % 16 == 0), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// orders generic-proxy accesses (ld/st) with async-proxy accesses (TMA / bulk copies) to global and shared memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // multicast variant: the box lands at the same shared-memory offset of every CTA in cta_mask and signals the mbarrier at
 // the same offset in each of them
 __device__ __forceinline__ void tma_load_4d_mc(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -311,6 +320,31 @@ __device__ __forceinline__ float erf_fast(float x) {
     poly = fmaf(poly, t, 0.254829592f);
     const float y = 1.0f - poly * t * __expf(-ax * ax);
     return copysignf(y, x);
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// erf GELU with the same Abramowitz-Stegun polynomial, written for the epilogue's instruction budget: bare MUFU rcp / ex2
+// (no range fix-up code), 13 FP32 pipe instructions per element
+__device__ __forceinline__ float gelu_erf_lean(float x) {
+    const float z = x * 0.70710678118654752f;
+    const float az = fabsf(z);
+    const float t = rcp_ftz(fmaf(0.3275911f, az, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float e = ex2_ftz(az * az * -1.4426950408889634f);
+    const float y = fmaf(-(poly * t), e, 1.0f);  // erf(|z|)
+    const float hx = 0.5f * x;
+    return fmaf(hx, copysignf(y, z), hx);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }

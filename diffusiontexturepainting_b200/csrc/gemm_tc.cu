@@ -220,6 +220,11 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// second bank of checkpoints (rows gridDim.x .. 2*gridDim.x-1 of the buffer): phases of the in-kernel split-K reduction
+#define DBG_MARK2(slot)                                                                                  \
+    do {                                                                                                 \
+        if (p.dbg != nullptr) p.dbg[static_cast<long long>(gridDim.x + blockIdx.x) * 8 + (slot)] = gtime(); \
+    } while (0)
 #define DBG_MARK(slot)                                                                     \
     do {                                                                                   \
         if (p.dbg != nullptr) p.dbg[static_cast<long long>(blockIdx.x) * 8 + (slot)] = gtime(); \
@@ -309,7 +314,8 @@ __global__ void __launch_bounds__(320, OCC)
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-    uint64_t* peer_full_bar = tmem_empty_bar + 2;   // [STAGES] leader only: the peer CTA's operands of a stage have landed
+    uint64_t* peer_full_bar = tmem_empty_bar + 2;   // [STAGES] spare; [0] = completion of the split-K slice copies
+    uint64_t* red_bar = peer_full_bar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full_bar + STAGES);
     int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);  // split-K arrival ticket of the current tile (epilogue warps)
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
@@ -498,6 +504,15 @@ __global__ void __launch_bounds__(320, OCC)
         uint32_t acc_phase = 0;
         const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
         const bool fused_reduce = p.splits > 1 && p.tile_counters != nullptr;
+        // 32-byte aligned full-width fp16 rows (st.global.v8 / 16-byte residual loads) and an epilogue the fast path covers
+        const bool fast_epi =
+            OCC == 1 && p.splits == 1 && p.dbg_mode == 0 && (p.N & 31) == 0 && (p.ldc & 15) == 0 &&
+            (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 && ((p.out_zs1 | p.out_zs2) & 15) == 0 &&
+            ((p.flags & ~(GEMM_B_MN | GEMM_W_BLOCKED | GEMM_HINT_CL2)) == 0
+                 ? (p.residual == nullptr || ((p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 &&
+                                              ((p.res_zs1 | p.res_zs2) & 7) == 0))
+                 : ((p.flags & ~(GEMM_B_MN | GEMM_W_BLOCKED | GEMM_HINT_CL2)) == EPI_GEGLU && p.residual == nullptr &&
+                    (p.ldc & 31) == 0));
         for (int t = tile0; t < total_tiles; t += tstep) {
             const TileCoord c = decode_tile<BN, CL>(p, t, rank);
             const int row = tile_row(p, c, r);
@@ -508,13 +523,113 @@ __global__ void __launch_bounds__(320, OCC)
                 for (int i = et; i < BN; i += 256) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
                 epi_bar_sync();
             }
-            mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
-            if (t == tile0 && et == 0) DBG_MARK(4);
-            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
             // chunks this warp owns: cc = 32*half, 32*half + 64, ... (bounded by the tile width and by N)
             int n_mine = 0;
             for (int cc = 32 * half; cc < BN && c.n0 + cc < p.N; cc += 64) ++n_mine;
+            const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            if (fast_epi) {
+                // ---- fast path (fp16 row-major output, bias, optional residual, or GEGLU; every chunk full and 16-byte
+                // aligned): the residual of ALL chunks is requested before waiting for the accumulator, so its L2 latency
+                // hides behind the mainloop, and the TMEM read of chunk i+1 is in flight while chunk i is processed.
+                constexpr int IT = (BN + 63) / 64;
+                constexpr int RD = IT < 2 ? IT : 2;  // residual chunks in flight (a ring: chunk it + RD is requested once chunk it is consumed)
+                uint4 rres[RD][4];
+                const bool has_res = p.residual != nullptr;
+                const __half* rrow = has_res && row >= 0
+                                         ? p.residual + res_off + static_cast<long long>(row) * p.ldr + c.n0 + 32 * half
+                                         : nullptr;
+#pragma unroll
+                for (int it = 0; it < RD; ++it) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        rres[it][i] = (rrow != nullptr && it < n_mine) ? __ldg(reinterpret_cast<const uint4*>(rrow + 64 * it) + i)
+                                                                       : make_uint4(0u, 0u, 0u, 0u);
+                }
+                mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                if (t == tile0 && et == 0) DBG_MARK(4);
+                // wide tiles keep one chunk of scores in registers (register budget: 168 per thread), narrow ones two
+                constexpr int RB = IT <= 2 ? 2 : 1;
+                uint32_t raw[RB][32];
+                if (n_mine > 0) tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(32 * half), raw[0]);
+#pragma unroll
+                for (int it = 0; it < IT; ++it) {
+                    if (it < n_mine) {
+                        const int cc = 32 * half + 64 * it;
+                        tmem_ld_wait();
+                        if (RB == 2 && it + 1 < IT && it + 1 < n_mine)
+                            tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc + 64), raw[(it + 1) % RB]);
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[it % RB][i]);
+                        if (RB == 1 && it + 1 < IT && it + 1 < n_mine)
+                            tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc + 64), raw[0]);
+                        const float* bc = sbias + cc;
+                        if (col_bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.alpha, bc[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                        }
+                        if (row >= 0) {
+                            if (p.flags & EPI_GEGLU) {
+                                uint32_t o[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    o[i] = pack_half2(v[2 * i] * gelu_erf_lean(v[16 + 2 * i]), v[2 * i + 1] * gelu_erf_lean(v[17 + 2 * i]));
+                                __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc +
+                                              ((c.n0 + cc) >> 1);
+                                st_global_v8(out, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+                            } else {
+                                if (has_res) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const __half2* h2 = reinterpret_cast<const __half2*>(&rres[it % RD][i]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float2 f = __half22float2(h2[j]);
+                                            v[8 * i + 2 * j] += f.x;
+                                            v[8 * i + 2 * j + 1] += f.y;
+                                        }
+                                    }
+                                    if (it + RD < IT && it + RD < n_mine) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i)
+                                            rres[it % RD][i] = __ldg(reinterpret_cast<const uint4*>(rrow + 64 * (it + RD)) + i);
+                                    }
+                                }
+                                __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc +
+                                              c.n0 + cc;
+#pragma unroll
+                                for (int i = 0; i < 2; ++i)
+                                    st_global_v8(out + 16 * i, pack_half2(v[16 * i + 0], v[16 * i + 1]),
+                                                 pack_half2(v[16 * i + 2], v[16 * i + 3]), pack_half2(v[16 * i + 4], v[16 * i + 5]),
+                                                 pack_half2(v[16 * i + 6], v[16 * i + 7]), pack_half2(v[16 * i + 8], v[16 * i + 9]),
+                                                 pack_half2(v[16 * i + 10], v[16 * i + 11]), pack_half2(v[16 * i + 12], v[16 * i + 13]),
+                                                 pack_half2(v[16 * i + 14], v[16 * i + 15]));
+                            }
+                        }
+                    }
+                }
+                // every TMEM read of this warp has completed (the last tmem_ld_wait above): hand the accumulator back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CL == 2 && rank == 1)
+                        mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                    else
+                        mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+                continue;
+            }
+            mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            if (t == tile0 && et == 0) DBG_MARK(4);
             if (n_mine == 0) {
                 // nothing to read for this warp in this tile: still hand the accumulator back
                 tc_fence_before();
@@ -577,46 +692,54 @@ __global__ void __launch_bounds__(320, OCC)
                 // the group's `splits` partials are visible, then reduces ITS row slice of the tile in split order
                 // (bit-reproducible) and runs the epilogue for that slice.
                 int* cnt = p.tile_counters + 2 * tile_group(p, c);
+                const int r0 = (c.zsplit * 128) / p.splits, r1 = ((c.zsplit + 1) * 128) / p.splits;
+                const uint32_t slice_bytes = static_cast<uint32_t>(r1 - r0) * BN * 4;
+                const float* wsg = p.workspace + static_cast<long long>(tile_group(p, c)) * p.splits * 128 * BN;
+                // operand stages are idle (this CTA has no further tile): [splits][rows of my slice][BN] staging, then the sums
+                float* stage_f = reinterpret_cast<float*>(smem);
+                float* ssum = stage_f + static_cast<size_t>(p.splits) * (r1 - r0) * BN;
+                if (et == 0) DBG_MARK2(0);
+                fence_proxy_async_all();  // my partial is read by the peers' bulk copies (async proxy)
                 __threadfence();
+                if (et == 0) DBG_MARK2(1);
                 epi_bar_sync();
                 if (et == 0) {
+                    DBG_MARK2(2);
                     atomicAdd(cnt, 1);
                     const long long t0 = clock64();
                     while (ld_acquire_gpu(cnt) < p.splits) {
                         if (clock64() - t0 > 8000000000LL) __trap();
                     }
+                    DBG_MARK2(3);
+                    fence_proxy_async_all();
+                    // all of the group's slices in flight at once: one bulk copy per split
+                    mbar_arrive_expect_tx(red_bar, static_cast<uint32_t>(p.splits) * slice_bytes);
+                    for (int sidx = 0; sidx < p.splits; ++sidx)
+                        bulk_load_1d(reinterpret_cast<uint8_t*>(stage_f) + static_cast<size_t>(sidx) * slice_bytes,
+                                     wsg + (static_cast<long long>(sidx) * 128 + r0) * BN, slice_bytes, red_bar);
                 }
-                epi_bar_sync();
-                __threadfence();
-                const int r0 = (c.zsplit * 128) / p.splits, r1 = ((c.zsplit + 1) * 128) / p.splits;
-                const float* wsg = p.workspace + static_cast<long long>(tile_group(p, c)) * p.splits * 128 * BN;
-                float* ssum = reinterpret_cast<float*>(smem);  // operand stages are idle: this CTA has no further tile
-                constexpr int P4 = BN / 4;                     // 16-byte pieces per tile row
-                for (int i = et; i < (r1 - r0) * P4; i += 256) {
-                    const int rl = i / P4, c4 = i - rl * P4;
-                    const float* src = wsg + static_cast<long long>(r0 + rl) * BN + c4 * 4;
-                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int s0 = 0; s0 < p.splits; s0 += 8) {
-                        float4 t4[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (s0 + j < p.splits)
-                                t4[j] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<long long>(s0 + j) * 128 * BN));
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (s0 + j < p.splits) {
-                                a4.x += t4[j].x;
-                                a4.y += t4[j].y;
-                                a4.z += t4[j].z;
-                                a4.w += t4[j].w;
-                            }
+                mbar_wait_bounded(red_bar, 0);
+                if (et == 0) DBG_MARK2(4);
+                constexpr int P4 = BN / 4;  // 16-byte pieces per tile row
+                const int npieces = (r1 - r0) * P4;
+                for (int i = et; i < npieces; i += 256) {
+                    const float4* src = reinterpret_cast<const float4*>(stage_f) + i;
+                    float4 a4 = src[0];
+                    for (int sidx = 1; sidx < p.splits; ++sidx) {
+                        const float4 t4 = src[static_cast<size_t>(sidx) * npieces];
+                        a4.x += t4.x;
+                        a4.y += t4.y;
+                        a4.z += t4.z;
+                        a4.w += t4.w;
                     }
                     // unit u = (row, 32-column chunk) occupies 128 B; its 16-B pieces are XOR-swizzled by the unit index
+                    const int rl = i / P4, c4 = i - rl * P4;
                     const int u = rl * (BN / 32) + (c4 >> 3);
                     *reinterpret_cast<float4*>(ssum + u * 32 + (((c4 & 7) ^ (u & 7)) << 2)) = a4;
                 }
                 epi_bar_sync();
                 if (et == 0) {
+                    DBG_MARK2(5);
                     // all CTAs of the group have passed their wait before the last one gets here: safe to clear both slots
                     if (atomicAdd(cnt + 1, 1) == p.splits - 1) {
                         cnt[0] = 0;
