@@ -482,6 +482,8 @@ __global__ void __launch_bounds__(384, 1)
         float m_used = -INFINITY, l = 0.0f;
         uint8_t* prow = sP + w * P_BYTES + r * 128;
         const int sw = r & 7;
+        const uint32_t prow_s = smem_u32(prow);  // 128-byte aligned: XOR with a value < 128 only touches the piece bits
+        const uint32_t sw16 = static_cast<uint32_t>(sw) << 4;
         const float sc = p.scale_log2;
         for (int j = 0; j < nblk; ++j) {
             fa_wait(&s_full[w], j & 1);
@@ -556,10 +558,12 @@ __global__ void __launch_bounds__(384, 1)
                 tmem_st_wait();
             }
             l += l0 + l1;
+            // explicit 32-bit shared-window addresses: (piece ^ sw) << 4 == (piece << 4) ^ (sw << 4), one LOP3 per store
 #pragma unroll
             for (int c = 0; c < 128; c += 8)
-                *reinterpret_cast<uint4*>(prow + (c >> 6) * 16384 + ((((c & 63) >> 3) ^ sw) << 4)) =
-                    make_uint4(pk[(c >> 1) + 0], pk[(c >> 1) + 1], pk[(c >> 1) + 2], pk[(c >> 1) + 3]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((prow_s + (c >> 6) * 16384) ^ ((((c & 63) >> 3) << 4) ^ sw16)),
+                             "r"(pk[(c >> 1) + 0]), "r"(pk[(c >> 1) + 1]), "r"(pk[(c >> 1) + 2]), "r"(pk[(c >> 1) + 3])
+                             : "memory");
             tc_fence_before();
             fence_proxy_async_smem();
             __syncwarp();
