@@ -663,13 +663,15 @@ __global__ void __launch_bounds__(320, OCC)
                     }
                 }
                 if (fused_reduce) {
-                    // tile-contiguous partial [group][split][128 rows][BN]: every row of the tile is written (padding rows too)
-                    float v[32];
+                    // tile-contiguous partial [group][split][128 rows][BN] (padding rows are never read back into an output)
+                    if (row >= 0) {
+                        float v[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    float* ws = p.workspace +
-                                ((static_cast<long long>(tile_group(p, c)) * p.splits + c.zsplit) * 128 + r) * BN + cc;
-                    store_f32_chunk(ws, v, 32, true);
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+                        float* ws = p.workspace +
+                                    ((static_cast<long long>(tile_group(p, c)) * p.splits + c.zsplit) * 128 + r) * BN + cc;
+                        store_f32_chunk(ws, v, 32, true);
+                    }
                 } else if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
                     float v[32];
 #pragma unroll
@@ -933,7 +935,8 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
                       const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked) {
     params_defaults(op->p);
     GemmParams& p = op->p;
-    BN = fix_bn(BN);
+    const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
+    BN = fix_bn(BN & ~GEMM_BN_PAIR);
     if (A1 != nullptr && (K0 % 64) != 0) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "dual-source linear needs K0 %% 64 == 0 (K0=%d)", K0);
         return -10;
@@ -959,7 +962,7 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
         op->mapA1 = op->mapA0;
     }
     op->cluster = 1;
-    if (!w_blocked && gemm_cluster_enabled() && op->grid_m >= 2 && BN >= 32) {
+    if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
         if (map_rows(&op->mapBh, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN / 2)) return -13;
         op->cluster = 2;
     }
@@ -986,7 +989,8 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
                        const __half* Wt, int Cout, int BN, int splits, int w_blocked) {
     params_defaults(op->p);
     GemmParams& p = op->p;
-    BN = fix_bn(BN);
+    const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
+    BN = fix_bn(BN & ~GEMM_BN_PAIR);
     if ((C0 % 64) != 0 || (A1 != nullptr && (C1 % 64) != 0)) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "conv3x3 needs channel counts %% 64 == 0 (C0=%d C1=%d)", C0, C1);
         return -11;
@@ -1031,7 +1035,7 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
         op->mapA1 = op->mapA0;
     }
     op->cluster = 1;
-    if (!w_blocked && gemm_cluster_enabled() && op->grid_m >= 2 && BN >= 32) {
+    if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
         if (map_rows(&op->mapBh, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN / 2)) return -13;
         op->cluster = 2;
     }
@@ -1050,7 +1054,7 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
                        long long b_zs1, long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, int BN) {
     params_defaults(op->p);
     GemmParams& p = op->p;
-    BN = fix_bn(BN);
+    BN = fix_bn(BN & ~GEMM_BN_PAIR);
     if (b_mn && BN < 64) BN = 64;
     if (b_mn && BN == 160) BN = 192;  // MN-major B is loaded in 64-column boxes
     p.M = M;

@@ -36,6 +36,10 @@ enum GemmFlags : int {
     EPI_SOFTMAX16 = 1 << 9,     // row softmax over the first `aux` columns of every 16-column group (folded cross-attention)
 };
 
+// OR-ed into a BN argument / returned by gemm_pick_config in *BN: run the op as CTA pairs (cta_group::2, one 256-row MMA per
+// pair of m-tiles, each CTA fetching half of the weight tile). Ignored for problems with a single m-tile.
+constexpr int GEMM_BN_PAIR = 0x1000;
+
 struct GemmParams {
     int M, N;          // output rows per batch entry / output columns of the contraction
     int num_kb;        // number of 64-wide k blocks (all taps)

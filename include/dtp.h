@@ -57,7 +57,8 @@ const char* dtp_ops_last_error(void);
 /* tuning aid: per-CTA globaltimer checkpoints of the contraction kernel (see csrc/capi_ops.cu); NULL disables */
 void dtp_ops_set_debug_buffer(long long* dbg);
 
-/* out[M,N] = epilogue(alpha * [A0 | A1][M,K0+K1] * Wt[N,K0+K1]^T + bias) (+ residual). BN<=0: pick tile/split. */
+/* out[M,N] = epilogue(alpha * [A0 | A1][M,K0+K1] * Wt[N,K0+K1]^T + bias) (+ residual). BN<=0: pick tile/split.
+ * BN | 0x1000 runs the problem as CTA pairs (cta_group::2 MMA over two m-tiles, each CTA fetching half of the weight tile). */
 int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, int K1, int M, const void* Wt, int ldw,
                   int N, const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
                   int hw_out, int BN, int splits, void* stream);

@@ -42,6 +42,27 @@ def ring(nbytes):
     return max(1, min(24, int(300e6 // nbytes)))
 
 
+PAIR = 0x1000  # GEMM_BN_PAIR: run as CTA pairs (cta_group::2)
+SPLITS = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16)
+
+
+def configs(M, N, K):
+    """(BN, split-K) candidates; pair mode doubles the list for problems with at least two 128-row tiles. Split-K only where
+    the whole grid is co-resident (the in-kernel reduction) or nearly so."""
+    mt = (M + 127) // 128
+    for BN in (32, 64, 128, 160, 192, 256):
+        if BN > 64 and BN - 32 >= N:
+            continue
+        if BN == 32 and N > 64:
+            continue
+        gn = (N + BN - 1) // BN
+        for pair in ((0, PAIR) if (mt >= 2 and BN >= 64) else (0,)):
+            for sp in SPLITS:
+                if sp > 1 and ((K // 64) // sp < 2 or mt * gn * sp > 160):
+                    continue
+                yield BN | pair, sp
+
+
 def sweep_linear(M, N, K, flags=0):
     nbuf = ring(N * K * 2)
     A = torch.randn(M, K, device=dev).half()
@@ -55,13 +76,8 @@ def sweep_linear(M, N, K, flags=0):
             nat.check_op(L.dtp_op_linear(nat.ptr(A), K, K, None, 0, 0, M, nat.ptr(Ws[i % nbuf]), K, N, nat.ptr(bias), None, 0,
                                          nat.ptr(out), out.shape[1], flags, 1.0, 0, BN, sp, nat.stream_ptr()))
         return f
-    for BN in (32, 64, 128, 160, 192, 256):
-        if BN > 64 and BN - 32 >= N:
-            continue
-        for sp in (1, 2, 3, 4, 6, 8, 12, 16):
-            if sp > 1 and (K // 64) // sp < 2:
-                continue
-            res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
+    for BN, sp in configs(M, N, K):
+        res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
     auto = timeit(mk(0, 1), nbuf)
     report(f"linear M={M} N={N} K={K} flags={flags}", res, auto, 2.0 * M * N * K)
 
@@ -79,13 +95,8 @@ def sweep_conv(n, H, Wd, cin, cout):
             nat.check_op(L.dtp_op_conv3x3(nat.ptr(x), cin, None, 0, n, H, Wd, nat.ptr(ws[i % nbuf]), cout, nat.ptr(bias), None, 0,
                                           nat.ptr(out), cout, 0, 1.0, 0, BN, sp, nat.stream_ptr()))
         return f
-    for BN in (32, 64, 128, 160, 192, 256):
-        if BN > 64 and BN - 32 >= cout:
-            continue
-        for sp in (1, 2, 3, 4, 6, 8, 12, 16):
-            if sp > 1 and (9 * cin // 64) // sp < 2:
-                continue
-            res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
+    for BN, sp in configs(n * H * Wd, cout, 9 * cin):
+        res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
     auto = timeit(mk(0, 1), nbuf)
     report(f"conv3x3 n={n} {H}x{Wd} cin={cin} cout={cout} (M={n*H*Wd} K={9*cin})", res, auto,
            2.0 * n * H * Wd * cout * 9 * cin)
@@ -101,7 +112,7 @@ def report(name, res, auto, flops):
         CSV.write(f"{name};0;0;{auto:.2f}\n")
         CSV.flush()
     best = sorted(res.items(), key=lambda kv: kv[1])[:5]
-    s = ", ".join(f"BN={k[0]} sp={k[1]}: {v:.1f}us" for k, v in best)
+    s = ", ".join(f"BN={k[0] & 0xfff}{'p' if k[0] & PAIR else ''} sp={k[1]}: {v:.1f}us" for k, v in best)
     print(f"{name}: auto {auto:.1f}us ({flops / auto / 1e6:.0f} TF) | best {s} ({flops / best[0][1] / 1e6:.0f} TF)",
           flush=True)
 
@@ -130,6 +141,14 @@ if __name__ == "__main__":
             sweep_linear(*shp, flags=8)
         for shp in [(3, 32, 32, 320, 320), (3, 32, 32, 640, 320), (3, 32, 32, 960, 320), (3, 16, 16, 640, 640),
                     (3, 16, 16, 1280, 640), (3, 16, 16, 960, 640), (3, 4, 4, 1280, 1280), (3, 4, 4, 2560, 1280)]:
+            sweep_conv(*shp)
+    if which in ("all", "extra"):  # remaining shapes of the 512x512 stamp plan (UNet skip widths, conv_in, VAE levels)
+        for shp in [(12288, 320, 960), (3072, 640, 1920), (768, 1280, 1920), (3072, 640, 960), (768, 1280, 640),
+                    (3072, 640, 320)]:
+            sweep_linear(*shp)
+        for shp in [(3, 64, 64, 64, 320), (1, 512, 512, 128, 128), (1, 128, 128, 512, 512), (1, 256, 256, 256, 256),
+                    (1, 64, 64, 512, 512), (2, 64, 64, 512, 512), (1, 256, 256, 512, 256), (1, 256, 256, 512, 512),
+                    (1, 512, 512, 256, 256)]:
             sweep_conv(*shp)
     if which in ("all", "vae"):
         for shp in [(2, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:

@@ -141,7 +141,11 @@ def test_conv3x3(n, H, W, cin, cout):
     assert rel_l2(out, conv_ref(x, w, cin, b)) < 2e-3
 
 
-@pytest.mark.parametrize("splits,BN", [(1, 128), (4, 128), (3, 64), (2, 256), (1, 160), (2, 192)])
+PAIR = 0x1000  # GEMM_BN_PAIR: CTA-pair (cta_group::2) mode, selected per op through the BN argument
+
+
+@pytest.mark.parametrize("splits,BN", [(1, 128), (4, 128), (3, 64), (2, 256), (1, 160), (2, 192), (1, 128 | PAIR),
+                                       (2, 256 | PAIR), (3, 64 | PAIR), (5, 160 | PAIR)])
 def test_conv3x3_dual_source_residual_splitk(splits, BN):
     n, H, W, c0, c1, cout = 3, 8, 8, 128, 64, 256
     x0, x1 = h(rnd(n, H, W, c0)), h(rnd(n, H, W, c1, seed=5))
