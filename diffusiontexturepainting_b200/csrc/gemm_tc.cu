@@ -276,6 +276,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 __device__ __forceinline__ int tile_group(const GemmParams& p, const TileCoord& c) {
     return (c.zb * p.grid_n + c.n_tile) * p.grid_m + c.m_tile;
 }
+// Tile of persistent wave k for CTA (pair) `slot` of `nslots`: waves alternate direction, so the CTAs that got the cheap
+// tail tiles of one wave (tiles are ordered n-tile-major: full-width tiles first, the ragged last n-tile at the end) get
+// the first tiles of the next one. -1 past the end.
+__device__ __forceinline__ int tile_of_wave(int k, int slot, int nslots, int total) {
+    const int t = k * nslots + ((k & 1) ? nslots - 1 - slot : slot);
+    return t < total ? t : -1;
+}
 // output row (NHWC pixel index / matrix row) of tile-local row r, or -1 when r is padding
 __device__ __forceinline__ int tile_row(const GemmParams& p, const TileCoord& c, int r) {
     if (p.mode == 1) {
@@ -298,7 +305,8 @@ __device__ __forceinline__ int tile_row(const GemmParams& p, const TileCoord& c,
 template <int BN, int STAGES, int CL, int OCC = 1>
 __global__ void __launch_bounds__(320, OCC)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ GemmParams p) {
+                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBL,
+                   const __grid_constant__ GemmParams p) {
     // CL == 2: CTA pair (cta_group::2). One MMA spans both SMs (M = 256); each CTA's shared memory holds its own 128 rows
     // of A and HALF of the B tile (rows [rank*BN/2, +BN/2)), which halves the shared-memory traffic per CTA - the limit of
     // the single-CTA mainloop (TMA write + MMA read of A and B exceed 128 B/clk for wide tiles).
@@ -306,6 +314,12 @@ __global__ void __launch_bounds__(320, OCC)
     constexpr int B_BYTES = (BN / CL) * 128;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    // BN = 320 (CTA pairs only): one tile = two MMAs of N = 160 per k-step on the same A tile, a single 320-column
+    // accumulator (no double buffering); the weight tile is two 160-row sub-tiles, each split between the CTAs of the pair.
+    constexpr int NSUB = BN > 256 ? 2 : 1;
+    constexpr int BNS = BN / NSUB;
+    constexpr int NACC = (2 * BN <= 512) ? 2 : 1;
+    static_assert(NSUB == 1 || CL == 2, "tiles wider than 256 columns exist in pair mode only");
     constexpr int B_CHUNKS = (BN + 63) / 64;  // MN-major B: 64-column boxes
 
     extern __shared__ uint8_t smem_raw[];
@@ -335,6 +349,7 @@ __global__ void __launch_bounds__(320, OCC)
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapB);
+        if (p.n_last > 0) tma_prefetch_desc(&mapBL);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -370,34 +385,48 @@ __global__ void __launch_bounds__(320, OCC)
             // STAGES tiles are requested BEFORE waiting for the predecessor kernel, hiding the DRAM latency of
             // weight-streaming layers behind the previous kernel's tail. Activations (A) are only touched after the wait.
             int pre = 0;
-            constexpr int BH = BN / CL;  // rows of the B tile this CTA fetches (pair mode: its half)
             if (!p.b_batched && !b_mn && tile0 < total_tiles) {
                 const TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
+                const bool ragged0 = p.n_last > 0 && c0.n_tile == p.grid_n - 1;
+                const CUtensorMap* mB0 = ragged0 ? &mapBL : &mapB;
+                const uint32_t b0_bytes = ragged0 ? static_cast<uint32_t>(p.n_last / CL) * 128u : b_bytes;
                 pre = min(STAGES, c0.kb_end - c0.kb_begin);
                 for (int s = 0; s < pre; ++s) {
                     // pair mode: the leader's barrier counts the operand bytes of both CTAs
-                    if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[s], CL * (a_bytes + b_bytes));
+                    if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[s], CL * (a_bytes + b0_bytes));
                     uint8_t* sbp = smem + s * STAGE_BYTES + A_BYTES;
-                    if (CL == 2)
-                        tma_load_4d_pair(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0 + rank * BH, 0, 0);
+                    if (CL == 2) {
+#pragma unroll
+                        for (int j = 0; j < NSUB; ++j)
+                            tma_load_4d_pair(sbp + j * (BNS / CL) * 128, mB0, &full_bar[s], (c0.kb_begin + s) * 64,
+                                             NSUB == 1 ? c0.n0 + rank * ((ragged0 ? p.n_last : BN) / CL)
+                                                       : c0.n0 + j * BNS + rank * (BNS / CL),
+                                             0, 0);
+                    }
                     else if (w_blocked)
                         tma_load_4d(sbp, &mapB, &full_bar[s], 0, 0, c0.kb_begin + s, c0.n0 >> 6);
                     else
-                        tma_load_4d(sbp, &mapB, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
+                        tma_load_4d(sbp, mB0, &full_bar[s], (c0.kb_begin + s) * 64, c0.n0, 0, 0);
                 }
             }
             pdl_wait();
-            for (int t = tile0; t < total_tiles; t += tstep) {
+            for (int wave = 0;; ++wave) {
+                const int t = tile_of_wave(wave, tile0, tstep, total_tiles);
+                if (t < 0) break;
                 const TileCoord c = decode_tile<BN, CL>(p, t, rank);
                 const int za = p.a_batched ? c.z1 : 0, za2 = p.a_batched ? c.z2 : 0;
                 const int bz1 = p.b_batched ? c.z1 : 0, bz2 = p.b_batched ? c.z2 : 0;
+                const bool ragged = p.n_last > 0 && c.n_tile == p.grid_n - 1;
+                const CUtensorMap* mB = ragged ? &mapBL : &mapB;
+                const uint32_t tile_b_bytes = ragged ? static_cast<uint32_t>(p.n_last / CL) * 128u : b_bytes;
+                const int brow = c.n0 + rank * ((ragged ? p.n_last : BN) / CL);
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
-                    const bool prefetched = (t == tile0) && (kb - c.kb_begin) < pre;
+                    const bool prefetched = (wave == 0) && (kb - c.kb_begin) < pre;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     if (!prefetched) {
                         mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
-                        if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CL * (a_bytes + b_bytes));
+                        if (CL == 1 || rank == 0) mbar_arrive_expect_tx(&full_bar[stage], CL * (a_bytes + tile_b_bytes));
                     }
                     if (p.mode == 1) {
                         const int tap = kb / p.cblocks;
@@ -417,11 +446,14 @@ __global__ void __launch_bounds__(320, OCC)
                     if (prefetched) {
                         // B tile of this stage is already in flight
                     } else if (CL == 2) {
-                        tma_load_4d_pair(sb, &mapB, &full_bar[stage], kb * 64, c.n0 + rank * BH, 0, 0);
+#pragma unroll
+                        for (int j = 0; j < NSUB; ++j)
+                            tma_load_4d_pair(sb + j * (BNS / CL) * 128, mB, &full_bar[stage], kb * 64,
+                                             NSUB == 1 ? brow : c.n0 + j * BNS + rank * (BNS / CL), 0, 0);
                     } else if (w_blocked) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
-                        tma_load_4d(sb, &mapB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
+                        tma_load_4d(sb, mB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
                     } else {
 #pragma unroll
                         for (int j = 0; j < B_CHUNKS; ++j)
@@ -439,15 +471,19 @@ __global__ void __launch_bounds__(320, OCC)
             // peer CTA of a pair: its operands are consumed by the leader's MMAs (its TMA loads report to the leader's barriers)
         } else if (lane == 0) {
             // ------------------------------ MMA issuer (leader CTA in pair mode) ------------------------------
-            const uint32_t idesc = umma_idesc_f16(128 * CL, BN, 0, b_mn ? 1 : 0);
+            const uint32_t idesc_full = umma_idesc_f16(128 * CL, BNS, 0, b_mn ? 1 : 0);
+            const uint32_t idesc_last = umma_idesc_f16(128 * CL, p.n_last > 0 ? p.n_last : BN, 0, b_mn ? 1 : 0);
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             bool first = true;
-            for (int t = tile0; t < total_tiles; t += tstep) {
+            for (int wave = 0;; ++wave) {
+                const int t = tile_of_wave(wave, tile0, tstep, total_tiles);
+                if (t < 0) break;
                 const TileCoord c = decode_tile<BN, CL>(p, t, rank);
+                const uint32_t idesc = (p.n_last > 0 && c.n_tile == p.grid_n - 1) ? idesc_last : idesc_full;
                 mbar_wait_bounded(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -467,9 +503,13 @@ __global__ void __launch_bounds__(320, OCC)
                         // advance 16 K-elements: 32 B inside the swizzle atom (K-major) / two 8-row groups (MN-major)
                         const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
                         const uint64_t bd = bdesc + static_cast<uint64_t>(b_mn ? k * 128 : k * 2);
-                        if (CL == 2)
-                            umma_f16_2cta(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
-                        else
+                        if (CL == 2) {
+#pragma unroll
+                            for (int j = 0; j < NSUB; ++j)
+                                umma_f16_2cta(tmem_d + static_cast<uint32_t>(j * BNS),
+                                              ad, bd + static_cast<uint64_t>((j * (BNS / CL) * 128) >> 4), idesc,
+                                              (kb > c.kb_begin || k > 0) ? 1u : 0u);
+                        } else
                             umma_f16(tmem_d, ad, bd, idesc, (kb > c.kb_begin || k > 0) ? 1u : 0u);
                     }
                     if (CL == 2)
@@ -485,7 +525,7 @@ __global__ void __launch_bounds__(320, OCC)
                     umma_commit2_mc(&tmem_full_bar[acc], 3);  // wakes the epilogue warps of both CTAs
                 else
                     umma_commit(&tmem_full_bar[acc]);
-                if (++acc == 2) {
+                if (++acc == NACC) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -513,7 +553,9 @@ __global__ void __launch_bounds__(320, OCC)
                                               ((p.res_zs1 | p.res_zs2) & 7) == 0))
                  : ((p.flags & ~(GEMM_B_MN | GEMM_W_BLOCKED | GEMM_HINT_CL2)) == EPI_GEGLU && p.residual == nullptr &&
                     (p.ldc & 31) == 0));
-        for (int t = tile0; t < total_tiles; t += tstep) {
+        for (int wave = 0;; ++wave) {
+            const int t = tile_of_wave(wave, tile0, tstep, total_tiles);
+            if (t < 0) break;
             const TileCoord c = decode_tile<BN, CL>(p, t, rank);
             const int row = tile_row(p, c, r);
             const long long out_off = static_cast<long long>(c.z1) * p.out_zs1 + static_cast<long long>(c.z2) * p.out_zs2;
@@ -547,7 +589,7 @@ __global__ void __launch_bounds__(320, OCC)
                 }
                 mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
-                if (t == tile0 && et == 0) DBG_MARK(4);
+                if (wave == 0 && et == 0) DBG_MARK(4);
                 // wide tiles keep one chunk of scores in registers (register budget: 168 per thread), narrow ones two
                 constexpr int RB = IT <= 2 ? 2 : 1;
                 uint32_t raw[RB][32];
@@ -621,7 +663,7 @@ __global__ void __launch_bounds__(320, OCC)
                     else
                         mbar_arrive(&tmem_empty_bar[acc]);
                 }
-                if (++acc == 2) {
+                if (++acc == NACC) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
@@ -629,7 +671,7 @@ __global__ void __launch_bounds__(320, OCC)
             }
             mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            if (t == tile0 && et == 0) DBG_MARK(4);
+            if (wave == 0 && et == 0) DBG_MARK(4);
             if (n_mine == 0) {
                 // nothing to read for this warp in this tile: still hand the accumulator back
                 tc_fence_before();
@@ -765,7 +807,7 @@ __global__ void __launch_bounds__(320, OCC)
                     epilogue_store32(p, out_off, res_off, orow, col0, v, col_bias ? sbias + ch * 32 : nullptr);
                 }
             }
-            if (++acc == 2) {
+            if (++acc == NACC) {
                 acc = 0;
                 acc_phase ^= 1;
             }
@@ -912,8 +954,10 @@ static void params_defaults(GemmParams& p) {
 }
 
 static int fix_bn(int BN) {
-    return (BN == 32 || BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256) ? BN : 128;
+    return (BN == 32 || BN == 64 || BN == 128 || BN == 160 || BN == 192 || BN == 256 || BN == 320) ? BN : 128;
 }
+// BN = 320 exists for CTA pairs on problems whose N is a multiple of 320 (the UNet widths); anything else runs 256-wide
+static int legal_bn(int BN, bool pair_possible, int N) { return (BN == 320 && !(pair_possible && N % 320 == 0)) ? 256 : BN; }
 
 // 2-D (K inner, rows outer) map expressed as 4-D with unit batch dims
 static int map_rows(CUtensorMap* m, const __half* base, uint64_t K, uint64_t rows, uint64_t ld, uint32_t box_rows) {
@@ -931,12 +975,26 @@ static int map_blocked(CUtensorMap* m, const __half* base, uint64_t K, uint64_t 
     return make_map_4d(m, base, dims, st, box);
 }
 
+// Ragged last n-tile (N not a multiple of BN): its own weight box of n_last (pair mode: n_last / 2) rows
+static int setup_ragged(GemmOp* op, const __half* Wt, uint64_t K, uint64_t N, uint64_t ldw, int BN) {
+    GemmParams& p = op->p;
+    p.n_last = 0;
+    op->mapBL = (op->cluster == 2) ? op->mapBh : op->mapB;
+    const int rows_last = static_cast<int>(N % BN);
+    if (rows_last == 0) return 0;
+    const int n_last = (rows_last + 15) & ~15;
+    if (n_last >= BN) return 0;
+    if (map_rows(&op->mapBL, Wt, K, N, ldw, static_cast<uint32_t>(op->cluster == 2 ? n_last / 2 : n_last))) return -14;
+    p.n_last = n_last;
+    return 0;
+}
+
 int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
                       const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked) {
     params_defaults(op->p);
     GemmParams& p = op->p;
     const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
-    BN = fix_bn(BN & ~GEMM_BN_PAIR);
+    BN = legal_bn(fix_bn(BN & ~GEMM_BN_PAIR), want_pair && !w_blocked && M > 128, N);
     if (A1 != nullptr && (K0 % 64) != 0) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "dual-source linear needs K0 %% 64 == 0 (K0=%d)", K0);
         return -10;
@@ -963,7 +1021,7 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
     }
     op->cluster = 1;
     if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
-        if (map_rows(&op->mapBh, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN / 2)) return -13;
+        if (map_rows(&op->mapBh, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN > 256 ? BN / 4 : BN / 2)) return -13;
         op->cluster = 2;
     }
     if (w_blocked) {
@@ -973,9 +1031,16 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
             return -12;
         }
         p.flags |= GEMM_W_BLOCKED;
-        return map_blocked(&op->mapB, Wt, K, N, BN);
+        r = map_blocked(&op->mapB, Wt, K, N, BN);
+        op->mapBL = op->mapB;
+        return r;
     }
-    return map_rows(&op->mapB, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN);
+    if (BN > 256)
+        op->mapB = op->mapBh;  // pair-only tile width: the single-CTA box does not exist (and would exceed 256 rows)
+    else
+        r = map_rows(&op->mapB, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN);
+    if (r) return r;
+    return setup_ragged(op, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN);
 }
 
 static int largest_divisor_le(int n, int cap) {
@@ -991,6 +1056,7 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     GemmParams& p = op->p;
     const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
     BN = fix_bn(BN & ~GEMM_BN_PAIR);
+    if (BN == 320 && !(want_pair && !w_blocked && Cout % 320 == 0)) BN = 256;  // (single m-tile problems: checked below)
     if ((C0 % 64) != 0 || (A1 != nullptr && (C1 % 64) != 0)) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "conv3x3 needs channel counts %% 64 == 0 (C0=%d C1=%d)", C0, C1);
         return -11;
@@ -1018,6 +1084,10 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     p.ldc = Cout;
     op->BN = BN;
     op->grid_m = p.tiles_x * p.tiles_y * ((Nimg + p.bn - 1) / p.bn);
+    if (BN == 320 && op->grid_m < 2) {
+        BN = 256;
+        op->BN = 256;
+    }
     {
         uint64_t dims[4] = {(uint64_t)C0, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
         uint64_t st[3] = {(uint64_t)C0 * 2, (uint64_t)C0 * 2 * W, (uint64_t)C0 * 2 * W * H};
@@ -1036,7 +1106,7 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     }
     op->cluster = 1;
     if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
-        if (map_rows(&op->mapBh, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN / 2)) return -13;
+        if (map_rows(&op->mapBh, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN > 256 ? BN / 4 : BN / 2)) return -13;
         op->cluster = 2;
     }
     if (w_blocked) {
@@ -1045,9 +1115,17 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
             return -12;
         }
         p.flags |= GEMM_W_BLOCKED;
-        return map_blocked(&op->mapB, Wt, (uint64_t)9 * C, Cout, BN);
+        const int rb = map_blocked(&op->mapB, Wt, (uint64_t)9 * C, Cout, BN);
+        op->mapBL = op->mapB;
+        return rb;
     }
-    return map_rows(&op->mapB, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
+    int rm = 0;
+    if (BN > 256)
+        op->mapB = op->mapBh;
+    else
+        rm = map_rows(&op->mapB, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
+    if (rm) return rm;
+    return setup_ragged(op, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
 }
 
 int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, long long a_zs2, const __half* B, int ldb,
@@ -1055,6 +1133,7 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
     params_defaults(op->p);
     GemmParams& p = op->p;
     BN = fix_bn(BN & ~GEMM_BN_PAIR);
+    if (BN == 320) BN = 256;
     if (b_mn && BN < 64) BN = 64;
     if (b_mn && BN == 160) BN = 192;  // MN-major B is loaded in 64-column boxes
     p.M = M;
@@ -1086,12 +1165,16 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nz1, (uint64_t)nz2};
         uint64_t st[3] = {(uint64_t)ldb * 2, zstride(b_zs1, (uint64_t)ldb * 2 * N), zstride(b_zs2, (uint64_t)ldb * 2 * N)};
         uint32_t box[4] = {64, (uint32_t)BN, 1, 1};
-        return make_map_4d(&op->mapB, B, dims, st, box);
+        const int rk = make_map_4d(&op->mapB, B, dims, st, box);
+        op->mapBL = op->mapB;
+        return rk;
     } else {
         uint64_t dims[4] = {(uint64_t)N, (uint64_t)K, (uint64_t)nz1, (uint64_t)nz2};
         uint64_t st[3] = {(uint64_t)ldb * 2, zstride(b_zs1, (uint64_t)ldb * 2 * K), zstride(b_zs2, (uint64_t)ldb * 2 * K)};
         uint32_t box[4] = {64, 64, 1, 1};
-        return make_map_4d(&op->mapB, B, dims, st, box);
+        const int rk = make_map_4d(&op->mapB, B, dims, st, box);
+        op->mapBL = op->mapB;
+        return rk;
     }
 }
 
@@ -1218,6 +1301,7 @@ static bool splitk_fused(const GemmOp* op) {
     const long long gn = (p.N + op->BN - 1) / op->BN;
     const long long groups = static_cast<long long>(op->grid_m) * gn * p.nz1 * p.nz2;
     if (2 * groups > kTileCounterSlots) return false;
+    if (op->BN > 256 && p.splits < 4) return false;  // slice staging of the reduction must fit the operand stages
     if (op->cluster == 2) {
         const long long pair_tiles = static_cast<long long>((op->grid_m + 1) / 2) * gn * p.nz1 * p.nz2 * p.splits;
         return pair_tiles <= max_pair_clusters();
@@ -1262,7 +1346,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     const int cap = 2 * num_sms();
     p.tile_counters = (tiles <= cap && splitk_fused(op)) ? g_tile_counters : nullptr;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-    cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch (light): %s", cudaGetErrorString(e));
@@ -1323,10 +1407,10 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, p);
+        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, p);
     } else {
         const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-        e = launch_k(gemm_tc_kernel<BN, STAGES, 1>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, p);
+        e = launch_k(gemm_tc_kernel<BN, STAGES, 1>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, p);
     }
     if (e != cudaSuccess) e = cudaGetLastError();
     else e = cudaGetLastError();
@@ -1364,6 +1448,59 @@ static int max_pair_clusters() {
     return n;
 }
 
+// BN = 320: CTA pairs only (a single-CTA 128 x 320 tile would need 56 KB per stage)
+template <int BN, int STAGES2>
+static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
+    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
+    static_assert(SMEM2 <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) != cudaSuccess) {
+            snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute (pair): %s", cudaGetErrorString(cudaGetLastError()));
+            return -20;
+        }
+        attr_set = true;
+    }
+    if (op->cluster != 2) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "BN=%d needs pair mode", BN);
+        return -25;
+    }
+    GemmParams p = op->p;
+    p.dbg_mode = 0;
+    p.grid_m = op->grid_m;
+    p.grid_n = (p.N + BN - 1) / BN;
+    const long long tiles = static_cast<long long>((p.grid_m + 1) / 2) * p.grid_n * p.nz1 * p.nz2 * p.splits;
+    if (tiles > 0x7fffffffLL) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "too many tiles");
+        return -24;
+    }
+    p.total_tiles = static_cast<int>(tiles);
+    p.tile_counters = splitk_fused(op) ? g_tile_counters : nullptr;
+    const int max_clusters = num_sms() / 2;
+    const int nclusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = SMEM2;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, p);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch (pair): %s", cudaGetErrorString(e));
+        return -21;
+    }
+    return 0;
+}
+
 int gemm_launch(const GemmOp* op, cudaStream_t stream) {
     const GemmParams& p = op->p;
     if (p.splits > 1 && p.workspace == nullptr) {
@@ -1393,6 +1530,7 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
         case 128: r = launch_cfg<128, 6, 8>(op, stream); break;
         case 160: r = launch_cfg<160, 5, 7>(op, stream); break;
         case 192: r = launch_cfg<192, 5, 7>(op, stream); break;
+        case 320: r = launch_pair_only<320, 6>(op, stream); break;
         default: r = launch_cfg<256, 4, 6>(op, stream); break;
     }
     if (r) return r;

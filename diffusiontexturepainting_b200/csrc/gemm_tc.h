@@ -70,12 +70,15 @@ struct GemmParams {
     int* tile_counters;       // split-K arrival tickets, one per (batch, n-tile, m-tile); nullptr -> separate finalize launch
     long long* dbg;           // optional: per-CTA globaltimer checkpoints [ctas][8] (tuning aid), nullable
     int grid_m, grid_n, total_tiles;  // filled at launch: tile grid of the persistent scheduler
+    int n_last;        // > 0: the last n-tile is ragged; its MMAs use N = n_last (multiple of 16) and its weight box comes from
+                       // the op's mapBL (n_last rows; pair mode n_last / 2), so a narrow tail tile costs what it computes
     int dbg_mode;      // tuning aid (DTP_EPI_DEBUG): 1 = skip global stores, 2 = skip TMEM loads
 };
 
 struct GemmOp {
     CUtensorMap mapA0, mapA1, mapB;
-    CUtensorMap mapBh;  // B map with a BN/2-row box: each CTA of a 2-CTA cluster fetches one half and multicasts it
+    CUtensorMap mapBh;  // B map with a BN/2-row box: each CTA of a CTA pair fetches its half of the weight tile
+    CUtensorMap mapBL;  // B map of the ragged last n-tile (box rows = n_last, or n_last/2 in pair mode); == mapB / mapBh if none
     int cluster;        // 1 or 2
     GemmParams p;
     int BN;      // 32, 64, 128, 160, 192 or 256

@@ -50,13 +50,15 @@ def configs(M, N, K):
     """(BN, split-K) candidates; pair mode doubles the list for problems with at least two 128-row tiles. Split-K only where
     the whole grid is co-resident (the in-kernel reduction) or nearly so."""
     mt = (M + 127) // 128
-    for BN in (32, 64, 128, 160, 192, 256):
+    for BN in (32, 64, 128, 160, 192, 256, 320):
         if BN > 64 and BN - 32 >= N:
             continue
         if BN == 32 and N > 64:
             continue
+        if BN == 320 and (N % 320 or mt < 2):
+            continue
         gn = (N + BN - 1) // BN
-        for pair in ((0, PAIR) if (mt >= 2 and BN >= 64) else (0,)):
+        for pair in ((PAIR,) if BN == 320 else (0, PAIR) if (mt >= 2 and BN >= 64) else (0,)):
             for sp in SPLITS:
                 if sp > 1 and ((K // 64) // sp < 2 or mt * gn * sp > 160):
                     continue

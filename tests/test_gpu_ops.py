@@ -156,6 +156,17 @@ def test_conv3x3_dual_source_residual_splitk(splits, BN):
     assert rel_l2(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,splits", [(3, 16, 16, 128, 320, 1), (3, 32, 32, 64, 640, 1), (3, 8, 8, 256, 640, 4),
+                                                   (1, 64, 64, 64, 320, 1), (5, 16, 16, 64, 320, 1)])
+def test_conv3x3_wide_pair_tile(n, H, W, cin, cout, splits):
+    """BN = 320 CTA-pair tiles (two N = 160 MMAs per k-step into one 320-column accumulator), odd m-tile counts included."""
+    x = h(rnd(n, H, W, cin))
+    w = h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5))
+    b, r = rnd(cout), h(rnd(n, H, W, cout, seed=9))
+    out = conv_op(x, w, bias=b, residual=r, BN=320 | PAIR, splits=splits)
+    assert rel_l2(out, conv_ref(x, w, cin, b) + r.float()) < 2e-3
+
+
 def test_conv3x3_small_cout_f32_nchw():
     n, H, W, cin, cout = 3, 16, 16, 320, 4
     x, w, b = h(rnd(n, H, W, cin)), h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5)), rnd(cout)
