@@ -556,7 +556,8 @@ static int gn_sm_count() {
 
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
                      const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
-                     cudaStream_t st) {
+                     cudaStream_t st, int* launches) {
+    if (launches) *launches = 1;
     if (x1 == nullptr) C1 = 0;
     const int C = C0 + C1;
     if ((C0 % 8) || (C1 % 8) || (C % groups) || groups > 256) {
@@ -635,6 +636,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     launch_k(gn_stats_kernel, dim3(dim3(chunks, Nimg)), dim3(threads), smem, st, x0, C0, x1, C1, HW, groups, chunks, partial, counters,
                                                                gamma, beta, eps, coef);
     if (check_launch("gn_stats")) return -1;
+    if (launches) *launches = 2;
     const long long total_vec = static_cast<long long>(Nimg) * HW * CV;
     launch_k(gn_apply_kernel, dim3(static_cast<unsigned>((total_vec + 255) / 256)), dim3(256), 0, st, x0, C0, x1, C1, HW, total_vec, coef,
                                                                                    silu, out);

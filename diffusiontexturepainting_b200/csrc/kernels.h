@@ -18,7 +18,7 @@ int gn_num_chunks(int HW, int C);
 size_t gn_ws_floats(int Nimg, int HW, int C, int groups);
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
                      const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
-                     cudaStream_t st);
+                     cudaStream_t st, int* launches = nullptr);  // *launches: kernels enqueued (1 or 2)
 
 int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const float* beta, float eps, __half* out,
                      cudaStream_t st);

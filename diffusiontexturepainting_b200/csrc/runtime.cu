@@ -348,11 +348,12 @@ struct Builder {
         const int C0 = a0.C, C1 = a1.p ? a1.C : 0, Nimg = a0.N;
         __half* o = out.p;
         plan.add(K_GROUPNORM, [=](cudaStream_t st) -> int {
-            if (launch_groupnorm(x0, C0, x1, C1, Nimg, HW, groups, g, bt, eps, silu, o, ws, st)) {
+            int n_launched = 1;
+            if (launch_groupnorm(x0, C0, x1, C1, Nimg, HW, groups, g, bt, eps, silu, o, ws, st, &n_launched)) {
                 eng->err_ = kernels_last_error();
                 return -1;
             }
-            return 2;
+            return n_launched;
         }, "groupnorm rows=" + std::to_string(static_cast<long long>(Nimg) * HW) + " C=" + std::to_string(C0 + C1));
         release_raw(ws);  // stream-ordered: the next consumer of this slab runs after the norm
         return out;
