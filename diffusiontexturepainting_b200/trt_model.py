@@ -14,6 +14,7 @@ from . import weights as W
 from .image_encoder import ConditionPatchEncoder
 from .inpaint_pipeline import InpaintPipeline
 from .model_base import ConditionalInpainterBase
+from .serving import BrushCache
 
 
 def crop_resize_square(image, width):
@@ -63,6 +64,8 @@ class TRTConditionalInpainter(ConditionalInpainterBase):
         self.conditioning = None
         self.image = None
         self._device = device
+        # brush history of the client holds <= 10 brushes; set to None to re-encode on every switch
+        self.brush_cache = BrushCache(10)
 
     def device(self):
         return self._device
@@ -76,9 +79,16 @@ class TRTConditionalInpainter(ConditionalInpainterBase):
 
     def set_brush(self, image):
         """image: 3 x H x W float32 0..1 (trt_model.py:79-88)."""
-        self.image = crop_resize_square(image, width=self.resolution()).unsqueeze(0).to(self.pipeline.device).float() \
-            .contiguous()
-        self.conditioning = self.image_encoder.encode_image(self.image)
+        key = BrushCache.key(image, self.resolution()) if self.brush_cache is not None else None
+        hit = self.brush_cache.get(key) if key is not None else None
+        if hit is not None:
+            self.image, self.conditioning = hit
+        else:
+            self.image = crop_resize_square(image, width=self.resolution()).unsqueeze(0).to(self.pipeline.device) \
+                .float().contiguous()
+            self.conditioning = self.image_encoder.encode_image(self.image)
+            if key is not None:
+                self.brush_cache.put(key, (self.image, self.conditioning))
         self.pipeline.set_condition(*self.conditioning)
 
     @staticmethod
