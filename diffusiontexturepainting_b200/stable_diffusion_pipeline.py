@@ -96,25 +96,12 @@ def load_state_dicts(cfg, lora_path=None, seed=20240726):
     if cfg.name != "sd15-inpaint":
         return unet_sd, vae_sd, enc_sd
     hf = os.environ.get("DTP_HF_DIR", "./HF_cache/stable-diffusion-inpainting")
-
-    def try_load(path):
-        if not os.path.exists(path):
-            return None
-        if path.endswith(".safetensors"):
-            from safetensors.torch import load_file
-            return load_file(path)
-        return torch.load(path, map_location="cpu")
-
-    for sub, target in (("unet", unet_sd), ("vae", vae_sd)):
-        for fn in ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin"):
-            sd = try_load(os.path.join(hf, sub, fn))
-            if sd is not None:
-                target.update({k: v.float() for k, v in sd.items() if k in target})
-                break
-    lora = try_load(lora_path) if lora_path else None
-    if lora is not None:
-        unet_sd.update({k: v.float() for k, v in lora.items() if k in unet_sd})
-    enc = try_load(os.environ.get("DTP_IMAGE_ENCODER", "/workspace/checkpoints/image_encoder.pth"))
-    if enc is not None:
-        enc_sd.update({k: v.float() for k, v in enc.items() if k in enc_sd})
+    from .checkpoints import load_real_checkpoints
+    # a checkpoint file that exists must load completely (DTP_STRICT_WEIGHTS=0 downgrades that to a printed report)
+    strict = os.environ.get("DTP_STRICT_WEIGHTS", "1") != "0"
+    reports = load_real_checkpoints(unet_sd, vae_sd, enc_sd, hf, lora_path,
+                                    os.environ.get("DTP_IMAGE_ENCODER", "/workspace/checkpoints/image_encoder.pth"),
+                                    strict=strict)
+    for r in reports:
+        print("[dtp] " + r.summary())
     return unet_sd, vae_sd, enc_sd
