@@ -1,8 +1,11 @@
 // tcgen05 / TMEM / TMA contraction kernel for sm_100a. See gemm_tc.h for the problem statement.
 //
-// CTA = 192 threads: warp 0 (one lane) is the TMA producer, warp 1 allocates TMEM and (one lane) issues
-// tcgen05.mma, warps 2..5 are the epilogue (each owns the 32 TMEM lanes of its warp-id % 4 quarter).
-// Operand tiles are 128 x 64 (A) and BN x 64 (B) fp16, 128-byte swizzled, STAGES-deep mbarrier ring.
+// CTA = 320 threads: warp 0 (one lane) is the TMA producer, warp 1 allocates TMEM and (one lane) issues tcgen05.mma,
+// warps 2..9 are the epilogue (two per TMEM lane quarter, warp-id % 4, taking alternate 32-column chunks of the tile).
+// Operand tiles are 128 x 64 (A) and BN x 64 (B) fp16, 128-byte swizzled, STAGES-deep mbarrier ring; persistent tile loop
+// with two TMEM accumulators. CL = 2: CTA pairs (cta_group::2, one 256-row MMA per pair, each CTA fetching its 128 rows of
+// A and half of the weight tile); BN = 320 exists in pair mode only (two N = 160 MMAs per k-step, one accumulator).
+// Split-K partials are reduced inside the kernel when the host can guarantee one tile per CTA on a co-resident grid.
 #include "gemm_tc.h"
 
 #include <stdio.h>
