@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kctx.h"
 #include "gemm_tc.h"
 #include "kernels.h"
 
@@ -607,7 +608,8 @@ static int launch_flash2(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
                          cudaStream_t st) {
     constexpr int SMEM = DCH * 16384 * (2 + 2 * KS) + 4 * 16384 + (9 + 4 * KS) * 8 + 16 + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {false};
+    bool& attr_set = attr_set_dev[kctx_device()];
     if (!attr_set) {
         if (cudaFuncSetAttribute(flash_attn2_kernel<DCH, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
             cudaSuccess)
@@ -882,7 +884,8 @@ static int launch_flash3(const CUtensorMap& mq, const CUtensorMap& mk, const CUt
                          cudaStream_t st) {
     constexpr int SMEM = DCH * 16384 * (1 + 2 * KS) + 2 * 16384 + (8 + 4 * KS) * 8 + 16 + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {false};
+    bool& attr_set = attr_set_dev[kctx_device()];
     if (!attr_set) {
         if (cudaFuncSetAttribute(flash_attn3_kernel<DCH, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
             cudaSuccess)
@@ -898,7 +901,8 @@ static int launch_flash(const CUtensorMap& mq, const CUtensorMap& mk, const CUte
                         cudaStream_t st) {
     constexpr int SMEM = DCH * 16384 * (1 + 2 * KV_STAGES) + 2 * 16384 + (5 + 4 * KV_STAGES) * 8 + 16 + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {false};
+    bool& attr_set = attr_set_dev[kctx_device()];
     if (!attr_set) {
         if (cudaFuncSetAttribute(flash_attn_kernel<DCH, KV_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
             cudaSuccess)

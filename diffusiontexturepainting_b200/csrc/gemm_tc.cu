@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "kctx.h"
 
 namespace dtp {
 
@@ -755,7 +756,10 @@ __global__ void __launch_bounds__(320, OCC)
                     atomicAdd(cnt, 1);
                     const long long t0 = clock64();
                     while (ld_acquire_gpu(cnt) < p.splits) {
-                        if (clock64() - t0 > 8000000000LL) __trap();
+                        if (clock64() - t0 > 4000000000LL) {  // a CTA of the split group never became resident
+                            if (p.err_flag != nullptr) *p.err_flag = 2;
+                            break;
+                        }
                     }
                     DBG_MARK2(3);
                     fence_proxy_async_all();
@@ -948,6 +952,7 @@ bool gemm_cluster_enabled() {
     return on;
 }
 
+static void bind_ctx(GemmOp* op);
 static void params_defaults(GemmParams& p) {
     memset(&p, 0, sizeof(p));
     p.splits = 1;
@@ -1010,7 +1015,7 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
     p.cblocks0 = kb0;
     p.cblocks = kb0 + kb1;
     p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
-    if (p.splits > 1) gemm_prepare_splitk();
+    bind_ctx(op);
     p.ldc = N;
     op->BN = BN;
     op->grid_m = (M + 127) / 128;
@@ -1083,7 +1088,7 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     p.cblocks = C / 64;
     p.num_kb = 9 * p.cblocks;
     p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
-    if (p.splits > 1) gemm_prepare_splitk();
+    bind_ctx(op);
     p.ldc = Cout;
     op->BN = BN;
     op->grid_m = p.tiles_x * p.tiles_y * ((Nimg + p.bn - 1) / p.bn);
@@ -1154,6 +1159,7 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
     op->BN = BN;
     op->grid_m = (M + 127) / 128;
     op->cluster = 1;
+    bind_ctx(op);
     // size-1 batch dims still need a legal (multiple of 16 B) stride
     auto zstride = [](long long s, uint64_t fallback) -> uint64_t { return s > 0 ? (uint64_t)s * 2 : fallback; };
     {
@@ -1269,38 +1275,30 @@ void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* sp
 }
 
 // Arrival tickets of the fused split-K reduction: zeroed once, self-resetting afterwards (the last arriver of a tile clears
-// its slot), shared by all launches of a stream. Allocated from the setup functions, i.e. never during graph capture.
-static const int kTileCounterSlots = 1 << 16;
-static int* g_tile_counters = nullptr;
+// its slot), shared by all launches of a stream. They live in the KernelCtx of the engine that builds the op (kctx.h), are
+// captured into the op by the setup functions and therefore never allocated during graph capture.
 static int* tile_counters() {
     static const int on = []() {
         const char* e = getenv("DTP_SPLITK_FUSED");
         return (e && e[0] == '0') ? 0 : 1;
     }();
     if (!on) return nullptr;
-    if (g_tile_counters == nullptr) {
-        int* ptr = nullptr;
-        if (cudaMalloc(&ptr, kTileCounterSlots * sizeof(int)) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        if (cudaMemset(ptr, 0, kTileCounterSlots * sizeof(int)) != cudaSuccess) {
-            cudaGetLastError();
-            cudaFree(ptr);
-            return nullptr;
-        }
-        g_tile_counters = ptr;
-    }
-    return g_tile_counters;
+    KernelCtx* c = kctx_current();
+    return c ? c->tile_counters : nullptr;
 }
 void gemm_prepare_splitk() { (void)tile_counters(); }
+static void bind_ctx(GemmOp* op) {
+    KernelCtx* c = kctx_current();
+    op->tile_counters = op->p.splits > 1 ? tile_counters() : nullptr;
+    op->p.err_flag = c ? c->err_flag_dev : nullptr;
+}
 static int num_sms();
 static int max_pair_clusters();
 // The in-kernel split-K reduction waits for the other CTAs of a tile's split group, so it is only used when every CTA owns
 // exactly one tile and the whole grid is co-resident (tiles <= SMs; CTA pairs: <= the co-resident cluster count).
 static bool splitk_fused(const GemmOp* op) {
     const GemmParams& p = op->p;
-    if (p.splits <= 1 || g_tile_counters == nullptr) return false;
+    if (p.splits <= 1 || op->tile_counters == nullptr) return false;
     const long long gn = (p.N + op->BN - 1) / op->BN;
     const long long groups = static_cast<long long>(op->grid_m) * gn * p.nz1 * p.nz2;
     if (2 * groups > kTileCounterSlots) return false;
@@ -1314,21 +1312,22 @@ static bool splitk_fused(const GemmOp* op) {
 int gemm_num_launches(const GemmOp* op) { return (op->p.splits > 1 && !splitk_fused(op)) ? 2 : 1; }
 
 static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
+    KernelCtx* c = kctx_current();
+    return c ? c->sms : 148;
 }
+
+// cudaFuncSetAttribute applies to the current device's instance of the kernel: one flag per device ordinal
+struct PerDeviceFlag {
+    bool set[kMaxDevices] = {false};
+    bool& here() { return set[kctx_device()]; }
+};
 
 template <int BN, int STAGES>
 static int launch_light(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
     static_assert(SMEM <= 113 * 1024 && 2 * BN <= 256, "two CTAs per SM");
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+    bool& attr_set = attr_flag.here();
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute (light): %s", cudaGetErrorString(cudaGetLastError()));
@@ -1347,7 +1346,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     const int cap = 2 * num_sms();
-    p.tile_counters = (tiles <= cap && splitk_fused(op)) ? g_tile_counters : nullptr;
+    p.tile_counters = (tiles <= cap && splitk_fused(op)) ? op->tile_counters : nullptr;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
     cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, p);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1363,7 +1362,8 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
     constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
     static_assert(SMEM <= 227 * 1024 && SMEM2 <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+    bool& attr_set = attr_flag.here();
     if (!attr_set) {
         cudaError_t e =
             cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -1391,7 +1391,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         return -24;
     }
     p.total_tiles = static_cast<int>(tiles);
-    p.tile_counters = splitk_fused(op) ? g_tile_counters : nullptr;
+    p.tile_counters = splitk_fused(op) ? op->tile_counters : nullptr;
     cudaError_t e;
     if (cl == 2) {
         const int max_clusters = num_sms() / 2;  // (fused split-K additionally requires tiles <= max_pair_clusters())
@@ -1426,7 +1426,9 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
 
 // co-resident 2-CTA clusters of the pair-mode kernel (one CTA per SM for every instantiation; queried on one of them)
 static int max_pair_clusters() {
-    static int n = -1;
+    KernelCtx* kc = kctx_current();
+    int local = -1;
+    int& n = kc ? kc->max_pair_clusters : local;
     if (n < 0) {
         constexpr int SMEM2 = 8 * (128 * 128 + 128 * 64) + (3 * 8 + 4) * 8 + 16 + 128 * 4 + 1024;
         cudaFuncSetAttribute(gemm_tc_kernel<128, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
@@ -1456,7 +1458,8 @@ template <int BN, int STAGES2>
 static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
     static_assert(SMEM2 <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
+    static PerDeviceFlag attr_flag;
+    bool& attr_set = attr_flag.here();
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute (pair): %s", cudaGetErrorString(cudaGetLastError()));
@@ -1478,7 +1481,7 @@ static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
         return -24;
     }
     p.total_tiles = static_cast<int>(tiles);
-    p.tile_counters = splitk_fused(op) ? g_tile_counters : nullptr;
+    p.tile_counters = splitk_fused(op) ? op->tile_counters : nullptr;
     const int max_clusters = num_sms() / 2;
     const int nclusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
     cudaLaunchConfig_t cfg = {};

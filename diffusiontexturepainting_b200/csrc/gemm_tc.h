@@ -73,6 +73,7 @@ struct GemmParams {
     int n_last;        // > 0: the last n-tile is ragged; its MMAs use N = n_last (multiple of 16) and its weight box comes from
                        // the op's mapBL (n_last rows; pair mode n_last / 2), so a narrow tail tile costs what it computes
     int dbg_mode;      // tuning aid (DTP_EPI_DEBUG): 1 = skip global stores, 2 = skip TMEM loads
+    int* err_flag;     // mapped host flag of the owning KernelCtx: set when a cross-CTA wait gives up (kctx.h)
 };
 
 struct GemmOp {
@@ -83,6 +84,7 @@ struct GemmOp {
     GemmParams p;
     int BN;      // 32, 64, 128, 160, 192 or 256
     int grid_m;  // number of 128-row tiles
+    int* tile_counters;  // split-K tickets of the KernelCtx current at setup time (nullptr: finalize kernel)
     int light;   // 1: two-CTAs-per-SM configuration (short K loops, BN <= 128); set by gemm_launch from the problem shape
 };
 

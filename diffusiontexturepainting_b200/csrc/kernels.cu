@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "kctx.h"
 
 namespace dtp {
 
@@ -79,20 +80,11 @@ size_t gn_ws_floats(int Nimg, int HW, int C, int groups) {
     return static_cast<size_t>(Nimg) * chunks * groups * 2 + static_cast<size_t>(Nimg) * C * 2 + 64;
 }
 
-static int* g_gn_counters = nullptr;  // self-resetting per-sample tickets (stream-ordered reuse)
+// self-resetting per-sample tickets (stream-ordered reuse) live in the current KernelCtx (kctx.h)
 static int gn_counters(int Nimg, int** out) {
-    static int cap = 0;
-    if (Nimg > cap) {
-        if (g_gn_counters) cudaFree(g_gn_counters);
-        cap = Nimg < 256 ? 256 : Nimg;
-        if (cudaMalloc(&g_gn_counters, cap * sizeof(int)) != cudaSuccess) {
-            cap = 0;
-            g_gn_counters = nullptr;
-            return -1;
-        }
-        cudaMemset(g_gn_counters, 0, cap * sizeof(int));
-    }
-    *out = g_gn_counters;
+    KernelCtx* c = kctx_current();
+    if (!c || Nimg > kGnSamples) return -1;
+    *out = c->gn_counters;
     return 0;
 }
 
@@ -326,20 +318,10 @@ __global__ void __launch_bounds__(256)
 // read from L2/HBM once and there is one launch instead of two.
 //   barrier state per sample: one monotonically growing arrival counter (see GN_BAR_QUANTUM); replaying the same launch
 //   (CUDA graph) needs no host-side reset.
-static unsigned* g_gn_barrier = nullptr;
 static int gn_barrier_state(int Nimg, unsigned** out) {
-    static int cap = 0;
-    if (Nimg > cap) {
-        if (g_gn_barrier) cudaFree(g_gn_barrier);
-        cap = Nimg < 256 ? 256 : Nimg;
-        if (cudaMalloc(&g_gn_barrier, cap * 2 * sizeof(unsigned)) != cudaSuccess) {
-            cap = 0;
-            g_gn_barrier = nullptr;
-            return -1;
-        }
-        cudaMemset(g_gn_barrier, 0, cap * 2 * sizeof(unsigned));
-    }
-    *out = g_gn_barrier;
+    KernelCtx* c = kctx_current();
+    if (!c || Nimg > kGnSamples) return -1;
+    *out = c->gn_barrier;
     return 0;
 }
 
@@ -360,7 +342,7 @@ __global__ void __launch_bounds__(512)
     gn_fused_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
                     int rpc, float* __restrict__ partial, unsigned* __restrict__ barrier,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                    __half* __restrict__ out, long long* __restrict__ dbg) {
+                    __half* __restrict__ out, long long* __restrict__ dbg, int* __restrict__ err_flag) {
     extern __shared__ __align__(16) unsigned char gn_smem[];
     __shared__ float s_stat[256][2];
     const int C = C0 + C1;
@@ -466,7 +448,10 @@ __global__ void __launch_bounds__(512)
         if (prev + w != target) {
             const long long t0 = clock64();
             while (static_cast<int>(ld_acquire_u32(barrier + n) - target) < 0) {
-                if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a CTA of this grid never became resident
+                if (clock64() - t0 > 4000000000LL) {  // ~2 s: a CTA of this grid never became resident (GPU shared?)
+                    if (err_flag != nullptr) *err_flag = 1;  // reported by the engine; the context stays alive
+                    break;
+                }
             }
         }
         __threadfence();
@@ -544,14 +529,8 @@ static int gn_fused_enabled() {
     return v;
 }
 static int gn_sm_count() {
-    static int v = 0;
-    if (!v) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        if (v <= 0) v = 148;
-    }
-    return v;
+    KernelCtx* c = kctx_current();
+    return c ? c->sms : 148;
 }
 
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
@@ -570,7 +549,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         return -1;
     }
     const int cpg = C / groups;
-    if (gn_fused_enabled() && CV <= 512 && Nimg <= gn_sm_count()) {
+    if (gn_fused_enabled() && CV <= 512 && Nimg <= gn_sm_count() && Nimg <= kGnSamples) {
         // block = CV * rows_per_iter threads, a multiple of 32 (the group reductions use full-warp shuffles)
         int gcd = CV, t32 = 32;
         while (t32) {
@@ -591,7 +570,8 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         cps = (HW + rpc - 1) / rpc;
         const size_t smem = static_cast<size_t>(rpc) * C * sizeof(__half) + static_cast<size_t>(rows_per_iter) * C * sizeof(float2);
         if (rows_per_iter >= 1 && smem <= 200 * 1024 && groups <= 256) {
-            static bool attr_set = false;
+            static bool attr_set_dev[kMaxDevices] = {false};
+            bool& attr_set = attr_set_dev[kctx_device()];
             if (!attr_set) {
                 if (cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
                     return check_launch("gn_fused attr");
@@ -603,7 +583,7 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
                 return -1;
             }
             launch_k(gn_fused_kernel, dim3(cps, Nimg), dim3(threads), smem, st, x0, C0, x1, C1, HW, groups, rpc, stats_ws, barrier,
-                     gamma, beta, eps, silu, out, g_kdbg);
+                     gamma, beta, eps, silu, out, g_kdbg, kctx_current()->err_flag_dev);
             return check_launch("gn_fused");
         }
     }

@@ -8,6 +8,8 @@
 
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.h"
 
 namespace dtp {
@@ -566,9 +568,19 @@ struct Builder {
 Engine::Engine(const dtp_config& cfg) : cfg_(cfg) {
     if (cfg_.arena_bytes == 0) cfg_.arena_bytes = 8ull << 30;
     if (cfg_.enc_tokens <= 0) cfg_.enc_tokens = 14;
+    device_ = kctx_device();
+    kctx_ = kctx_create();  // on the device current at dtp_create (include/dtp.h: a handle is bound to that device)
+    if (!kctx_) err_ = "allocation of the kernel synchronisation state failed";
 }
 
 Engine::~Engine() {
+    cudaDeviceSynchronize();
+    for (cudaEvent_t e : stage_pool_) cudaEventDestroy(e);
+    for (cudaEvent_t e : prof_.pool) cudaEventDestroy(e);
+    if (gstream_) cudaStreamDestroy(gstream_);
+    if (gev_in_) cudaEventDestroy(gev_in_);
+    if (gev_out_) cudaEventDestroy(gev_out_);
+    kctx_destroy(kctx_);
     if (g_infer_.exec) cudaGraphExecDestroy(g_infer_.exec);
     if (g_stamp_.exec) cudaGraphExecDestroy(g_stamp_.exec);
     for (auto& kv : w_)
@@ -601,6 +613,78 @@ int Engine::ensure_arena() {
         return fail("cudaMalloc of the " + std::to_string(cfg_.arena_bytes >> 20) + " MiB activation arena failed");
     arena_.init(arena_base_, cfg_.arena_bytes);
     return 0;
+}
+
+int Engine::grow_arena(size_t bytes) {
+    if (bytes <= cfg_.arena_bytes && arena_base_) return 0;
+    cudaDeviceSynchronize();
+    if (arena_base_) cudaFree(arena_base_);
+    arena_base_ = nullptr;
+    if (bytes > cfg_.arena_bytes) cfg_.arena_bytes = bytes;
+    // every plan holds pointers into the old slab
+    unet_plan_.clear();
+    vae_enc_plan_.clear();
+    vae_dec_plan_.clear();
+    enc_plan_.clear();
+    cond_plan_.clear();
+    g_infer_.key.clear();
+    g_stamp_.key.clear();
+    return ensure_arena();
+}
+
+int Engine::check_device_error() {
+    const int v = kctx_take_error(kctx_);
+    if (v == 0) return 0;
+    return fail(std::string("a cross-CTA wait (") + (v == 1 ? "GroupNorm barrier" : "split-K ticket") +
+                ") timed out in an earlier call: the kernel's CTAs were not co-resident (is the GPU shared with another "
+                "process or stream?); the results of that call are invalid");
+}
+
+void Engine::stage_begin(int stage, cudaStream_t st) {
+    if (opt_nvtx_) {
+        static const char* names[ST_NUM] = {"canvas_preprocess", "vae_encoder", "unet", "latent_step", "vae", "composite"};
+        nvtxRangePushA(names[stage]);
+    }
+    if (!opt_stage_timers_) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    while (stage_next_ + 2 > stage_pool_.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        stage_pool_.push_back(e);
+    }
+    StageRec r{stage, stage_pool_[stage_next_], stage_pool_[stage_next_ + 1]};
+    stage_next_ += 2;
+    cudaEventRecord(r.a, st);
+    stage_recs_.push_back(r);
+}
+
+void Engine::stage_end(int stage, cudaStream_t st) {
+    if (opt_nvtx_) nvtxRangePop();
+    if (!opt_stage_timers_) return;
+    for (size_t i = stage_recs_.size(); i-- > 0;)
+        if (stage_recs_[i].stage == stage) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone)
+                cudaEventRecord(stage_recs_[i].b, st);
+            return;
+        }
+}
+
+void Engine::stage_collect() {
+    if (stage_recs_.empty()) return;
+    cudaEventSynchronize(stage_recs_.back().b);
+    for (auto& r : stage_recs_) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            stage_us_[r.stage] += 1000.0 * ms;
+            stage_n_[r.stage] += 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    stage_recs_.clear();
+    stage_next_ = 0;
 }
 
 int Engine::ensure_ws() {
@@ -1603,7 +1687,7 @@ std::string Engine::schedule_key() const {
 
 int Engine::run_graphed(GraphSlot& slot, const std::string& key, const std::function<int(cudaStream_t)>& body,
                         cudaStream_t st) {
-    if (!opt_graph_ || prof_.on) return body(st);
+    if (!opt_graph_ || prof_.on || opt_stage_timers_) return body(st);
     if (slot.key != key) {
         if (slot.exec) cudaGraphExecDestroy(slot.exec);
         slot.exec = nullptr;
@@ -1663,7 +1747,7 @@ int Engine::infer(int B, int R, const float* masked_img, const float* mask, cons
     if (!finalized_ && finalize_weights()) return -1;
     if (!cond_set_) return fail("infer: call dtp_set_condition first");
     if (ensure_io(B, R)) return -1;
-    if (!opt_graph_ || prof_.on)
+    if (!opt_graph_ || prof_.on || opt_stage_timers_)
         return infer_body(B, R, masked_img, mask, ctx_img, ctx_mask, init_latents, vae_noise, out_images, st);
     // stage the caller's tensors at fixed addresses so the captured graph can be replayed
     const size_t plane = static_cast<size_t>(B) * R * R, hw = static_cast<size_t>(R / 8) * (R / 8);
@@ -1704,9 +1788,11 @@ int Engine::infer_body(int B, int R, const float* masked_img, const float* mask,
     const size_t img = static_cast<size_t>(B) * 3 * R * R;
     // both VAE encodes (masked image, context image) as one batch of 2B (inpaint_pipeline.py:125-126)
     float* both = pre_ + static_cast<size_t>(B) * 12 * R * R;
+    stage_begin(ST_VAE_ENC, st);
     KCHECK(launch_copy_f32(masked_img, both, img, st));
     KCHECK(launch_copy_f32(ctx_img, both + img, img, st));
     if (vae_encode(2 * B, R, both, vae_noise, lat2_, st)) return -1;
+    stage_end(ST_VAE_ENC, st);
     // masks: nearest /8, stacked [mask, mask, ctx_mask]; masked latents [ml, ml, cml] (inpaint_pipeline.py:114-116,136)
     KCHECK(launch_mask_nearest(mask, B, R, 8, mask3_, st));
     KCHECK(launch_copy_f32(mask3_, mask3_ + static_cast<size_t>(B) * hw, static_cast<long long>(B) * hw, st));
@@ -1719,10 +1805,16 @@ int Engine::infer_body(int B, int R, const float* masked_img, const float* mask,
     // denoising loop (stable_diffusion_pipeline.py:407-462)
     for (int i = 0; i < n_steps_; ++i) {
         const float tg = (i > tg_steps_ - 1) ? 0.0f : tg_w_;
+        stage_begin(ST_UNET, st);
         if (unet_forward(B, R, nullptr, lat_, mask3_, masked3_, i, nullptr, st)) return -1;
+        stage_end(ST_UNET, st);
+        stage_begin(ST_DDIM, st);
         KCHECK(launch_guidance_ddim(unet_eps_, lat_, lat_, B, 4 * hw, cfg_w_, tg, a_t_[i], a_prev_[i], st));
+        stage_end(ST_DDIM, st);
     }
+    stage_begin(ST_VAE_DEC, st);
     if (vae_decode(B, R, lat_, out_images, st)) return -1;
+    stage_end(ST_VAE_DEC, st);
     ++stamps_;
     return 0;
 }
@@ -1733,7 +1825,7 @@ int Engine::stamp(int B, int R, const float* canvas, const float* brush, int pad
     if (!finalized_ && finalize_weights()) return -1;
     if (!cond_set_) return fail("stamp: call dtp_set_condition first");
     if (ensure_io(B, R)) return -1;
-    if (!opt_graph_ || prof_.on)
+    if (!opt_graph_ || prof_.on || opt_stage_timers_)
         return stamp_body(B, R, canvas, brush, pad, init_latents, vae_noise, composite, out_f32, out_u8, st);
     const size_t plane = static_cast<size_t>(B) * R * R, hw = static_cast<size_t>(R / 8) * (R / 8);
     float* s_canvas = stage_;
@@ -1773,16 +1865,20 @@ int Engine::stamp_body(int B, int R, const float* canvas, const float* brush, in
     float* cmask = pre_ + 7 * plane;
     float* scratch = pre_ + 8 * plane;
     float* raw = pre_ + 9 * plane;
+    stage_begin(ST_PRE, st);
     if (launch_canvas_preprocess(canvas, brush, B, R, pad, masked, mask, ctx, cmask, scratch, st)) {
         err_ = kernels_last_error();
         return -1;
     }
     launches_ += 2;
+    stage_end(ST_PRE, st);
     float* dst = (composite || out_f32 == nullptr) ? raw : out_f32;
     if (infer_body(B, R, masked, mask, ctx, cmask, init_latents, vae_noise, dst, st)) return -1;
     if (composite || out_u8) {
         if (composite) {
+            stage_begin(ST_POST, st);
             KCHECK(launch_composite(canvas, raw, B, R, out_f32, out_u8, st));
+            stage_end(ST_POST, st);
         } else {
             return fail("stamp: uint8 output is only produced together with compositing");
         }
@@ -1799,6 +1895,14 @@ long long Engine::counter(const char* name) const {
     if (n == "graph_launches") return graph_launches_;
     if (n == "unet_plan_ops") return static_cast<long long>(unet_plan_.ops.size());
     if (n == "ws_bytes") return static_cast<long long>(ws_bytes_);
+    if (n == "device") return device_;
+    if (n.rfind("stage_us_", 0) == 0 || n.rfind("stage_n_", 0) == 0) {
+        const_cast<Engine*>(this)->stage_collect();
+        const bool is_us = n[6] == 'u';
+        const int k = atoi(n.c_str() + (is_us ? 9 : 8));
+        if (k < 0 || k >= ST_NUM) return -1;
+        return is_us ? static_cast<long long>(stage_us_[k]) : stage_n_[k];
+    }
     if (n.rfind("prof_us_", 0) == 0 || n.rfind("prof_n_", 0) == 0) {
         const_cast<Profiler&>(prof_).collect();
         const bool is_us = n[5] == 'u';
@@ -1858,6 +1962,20 @@ int Engine::set_option(const char* name, int value) {
         prof_.on = value != 0;
         return 0;
     }
+    if (n == "stage_timers") {
+        stage_collect();
+        for (int i = 0; i < ST_NUM; ++i) {
+            stage_us_[i] = 0;
+            stage_n_[i] = 0;
+        }
+        opt_stage_timers_ = value;
+        return 0;
+    }
+    if (n == "nvtx") {
+        opt_nvtx_ = value;
+        return 0;
+    }
+    if (n == "arena_mib") return grow_arena(static_cast<size_t>(value) << 20);
     return fail("unknown option " + n);
 }
 
@@ -1871,6 +1989,24 @@ struct dtp_engine {
     Engine* e;
 };
 static char g_create_err[256] = "";
+
+// Every entry point runs on the device the handle was created on, with the handle's kernel context current (kctx.h).
+struct ApiScope {
+    int prev_dev = -1;
+    dtp::KernelCtxScope k;
+    explicit ApiScope(Engine* e) : k(e->kctx()) {
+        if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
+        if (prev_dev != e->device()) cudaSetDevice(e->device());
+        else prev_dev = -1;
+    }
+    ~ApiScope() {
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
+    }
+};
+#define API_ENTER(h)                         \
+    if (!(h) || !(h)->e) return -1;          \
+    ApiScope api_scope_((h)->e);             \
+    if ((h)->e->check_device_error()) return -5
 
 extern "C" {
 
@@ -1890,52 +2026,84 @@ int dtp_create(const dtp_config* cfg, dtp_handle** out) {
     }
     dtp_handle* h = new dtp_engine;
     h->e = new Engine(*cfg);
+    if (!h->e->ok()) {
+        snprintf(g_create_err, sizeof(g_create_err), "%s", h->e->last_error());
+        delete h->e;
+        delete h;
+        return -4;
+    }
     *out = h;
     return 0;
 }
 void dtp_destroy(dtp_handle* h) {
     if (!h) return;
-    delete h->e;
+    {
+        ApiScope scope(h->e);
+        delete h->e;
+        h->e = nullptr;
+    }
     delete h;
 }
 const char* dtp_last_error(dtp_handle* h) { return h ? h->e->last_error() : g_create_err; }
 int dtp_set_tensor(dtp_handle* h, const char* name, const void* host_ptr, const long long* shape, int ndim, int dtype) {
+    API_ENTER(h);
     return h->e->set_tensor(name, host_ptr, reinterpret_cast<const int64_t*>(shape), ndim, dtype);
 }
-int dtp_finalize_weights(dtp_handle* h) { return h->e->finalize_weights(); }
+int dtp_finalize_weights(dtp_handle* h) {
+    API_ENTER(h);
+    return h->e->finalize_weights();
+}
 int dtp_encode_patches(dtp_handle* h, const float* patches, float* emb_out, void* stream, void*) {
+    API_ENTER(h);
     return h->e->encode_patches(patches, emb_out, (cudaStream_t)stream);
 }
 int dtp_set_condition(dtp_handle* h, const float* emb, const float* uncond, void* stream) {
+    API_ENTER(h);
     return h->e->set_condition(emb, uncond, (cudaStream_t)stream);
 }
 int dtp_set_schedule(dtp_handle* h, int n, const float* timesteps, const float* alpha_t, const float* alpha_prev,
                      float cfg, float tg, int tg_steps) {
+    API_ENTER(h);
     return h->e->set_schedule(n, timesteps, alpha_t, alpha_prev, cfg, tg, tg_steps);
 }
 int dtp_infer(dtp_handle* h, int B, int R, const float* masked_img, const float* mask, const float* ctx_img,
               const float* ctx_mask, const float* init_latents, const float* vae_noise, float* out_images, void* stream) {
+    API_ENTER(h);
     return h->e->infer(B, R, masked_img, mask, ctx_img, ctx_mask, init_latents, vae_noise, out_images,
                        (cudaStream_t)stream);
 }
 int dtp_stamp(dtp_handle* h, int B, int R, const float* canvas, const float* brush, int pad, const float* init_latents,
               const float* vae_noise, int composite, float* out_f32, unsigned char* out_u8, void* stream) {
+    API_ENTER(h);
     return h->e->stamp(B, R, canvas, brush, pad, init_latents, vae_noise, composite, out_f32, out_u8,
                        (cudaStream_t)stream);
 }
 int dtp_vae_encode(dtp_handle* h, int Nb, int R, const float* images, const float* noise, float* latents_out,
                    void* stream) {
+    API_ENTER(h);
     return h->e->vae_encode(Nb, R, images, noise, latents_out, (cudaStream_t)stream);
 }
 int dtp_vae_decode(dtp_handle* h, int B, int R, const float* latents, float* images_out, void* stream) {
+    API_ENTER(h);
     return h->e->vae_decode(B, R, latents, images_out, (cudaStream_t)stream);
 }
 int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const float*, const float*, int step,
                      float* eps_out, void* stream) {
+    API_ENTER(h);
     return h->e->unet_forward(B, R, sample, nullptr, nullptr, nullptr, step, eps_out, (cudaStream_t)stream);
 }
-long long dtp_get_counter(dtp_handle* h, const char* name) { return h->e->counter(name); }
-int dtp_set_option(dtp_handle* h, const char* name, int value) { return h->e->set_option(name, value); }
-int dtp_profile_dump(dtp_handle* h, const char* path) { return h->e->profile_dump(path); }
+long long dtp_get_counter(dtp_handle* h, const char* name) {
+    if (!h || !h->e) return -1;
+    ApiScope scope(h->e);
+    return h->e->counter(name);
+}
+int dtp_set_option(dtp_handle* h, const char* name, int value) {
+    API_ENTER(h);
+    return h->e->set_option(name, value);
+}
+int dtp_profile_dump(dtp_handle* h, const char* path) {
+    API_ENTER(h);
+    return h->e->profile_dump(path);
+}
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 
 #include "../../include/dtp.h"
 #include "gemm_tc.h"
+#include "kctx.h"
 
 namespace dtp {
 
@@ -129,6 +130,12 @@ class Engine {
     int set_option(const char* name, int value);
     int profile_dump(const char* path);
     const char* last_error() const { return err_.c_str(); }
+    KernelCtx* kctx() const { return kctx_; }
+    int device() const { return device_; }
+    bool ok() const { return kctx_ != nullptr; }
+    // called at the top of every C-ABI entry point: reports a cross-CTA wait that gave up during an earlier call
+    int check_device_error();
+    int grow_arena(size_t bytes);
     bool fold_cross() const { return opt_fold_cross_ != 0; }
     int tf_index(const std::string& prefix) const {
         for (size_t i = 0; i < tf_names_.size(); ++i)
@@ -228,7 +235,25 @@ class Engine {
     long long graph_launches_ = 0;
 
     long long launches_ = 0, stamps_ = 0;
+    // per-stage device timers (the reference's cudart events + NVTX ranges 'vae_encoder' / 'unet' / 'vae',
+    // stable_diffusion_pipeline.py:146-149,358-366,486-503); dtp_set_option("stage_timers" / "nvtx", 1), eager mode only
+    enum Stage { ST_PRE = 0, ST_VAE_ENC, ST_UNET, ST_DDIM, ST_VAE_DEC, ST_POST, ST_NUM };
+    struct StageRec {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<StageRec> stage_recs_;
+    std::vector<cudaEvent_t> stage_pool_;
+    size_t stage_next_ = 0;
+    double stage_us_[ST_NUM] = {0};
+    long long stage_n_[ST_NUM] = {0};
+    int opt_stage_timers_ = 0, opt_nvtx_ = 0;
+    void stage_begin(int stage, cudaStream_t st);
+    void stage_end(int stage, cudaStream_t st);
+    void stage_collect();
     Profiler prof_;
+    KernelCtx* kctx_ = nullptr;  // cross-CTA synchronisation state of this engine's kernels (kctx.h)
+    int device_ = 0;
     int opt_sync_check_ = 0;
     int opt_flash_ = 1;
 };

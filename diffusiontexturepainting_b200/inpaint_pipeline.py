@@ -42,7 +42,14 @@ class InpaintPipeline(StableDiffusionPipeline):
         """text_embeddings = cat([negative, prompt, prompt]).half() (inpaint_pipeline.py:140); the cross-attention K/V of
         all layers are projected once per brush instead of once per UNet call."""
         self.engine.set_condition(prompt, negative_prompt)
-        self._cond_key = (prompt.data_ptr(), negative_prompt.data_ptr(), prompt._version, negative_prompt._version)
+        # strong references + in-place version counters: a freed embedding's address can be handed to a new tensor by the
+        # caching allocator, so (data_ptr, _version) alone cannot tell two brushes apart
+        self._cond_ref = (prompt, negative_prompt, prompt._version, negative_prompt._version)
+
+    def _same_condition(self, prompt, negative_prompt):
+        r = getattr(self, "_cond_ref", None)
+        return (r is not None and r[0] is prompt and r[1] is negative_prompt and r[2] == prompt._version
+                and r[3] == negative_prompt._version)
 
     def infer(self, prompt, negative_prompt, input_image, mask_image, context_masked_image, context_mask, image_height,
               image_width, seed=None, strength=1.0, verbose=False, init_latents=None, vae_noise=None):
@@ -52,8 +59,7 @@ class InpaintPipeline(StableDiffusionPipeline):
             raise ValueError("square patches only")
         B = input_image.shape[0]  # the reference derives it from the (1,14,768) prompt and only works for 1
         h = image_height // 8
-        key = (prompt.data_ptr(), negative_prompt.data_ptr(), prompt._version, negative_prompt._version)
-        if getattr(self, "_cond_key", None) != key:
+        if not self._same_condition(prompt, negative_prompt):
             self.set_condition(prompt, negative_prompt)
         if init_latents is None:
             init_latents = self.initialize_latents(B, 4, h, h)

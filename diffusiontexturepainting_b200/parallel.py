@@ -61,20 +61,64 @@ def broadcast_packed(packed: Optional[Dict[str, torch.Tensor]], device, src: int
     return out
 
 
-def scatter_stamps(full: Optional[torch.Tensor], shape_per_rank, dtype, device, src: int = 0) -> torch.Tensor:
-    """Rank `src` holds (world * b, ...) ; every rank receives its (b, ...) slice."""
+def _shard_sizes(total: Optional[int], world: int, local_n: int):
+    if total is None:
+        return [local_n] * world
+    return [b - a for a, b in (shard_range(total, r, world) for r in range(world))]
+
+
+def scatter_stamps(full: Optional[torch.Tensor], shape_per_rank, dtype, device, src: int = 0,
+                   total: Optional[int] = None) -> torch.Tensor:
+    """Rank `src` holds (n, ...) stamps; rank r receives rows shard_range(n, r, world) into a buffer of `shape_per_rank`.
+    `total` = n must be passed (on every rank) when n is not a multiple of the world size: the shards are then uneven (the
+    first n % world ranks hold one more) and travel point to point; an even split is one scatter."""
     out = torch.empty(shape_per_rank, dtype=dtype, device=device)
     if not dist.is_initialized() or dist.get_world_size() == 1:
         out.copy_(full)
         return out
-    chunks = list(full.chunk(dist.get_world_size())) if dist.get_rank() == src else None
-    dist.scatter(out, chunks, src=src)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = _shard_sizes(total, world, int(out.shape[0]))
+    if sizes[rank] != out.shape[0]:
+        raise ValueError(f"rank {rank}: shard of {sizes[rank]} stamps does not fit a buffer of {out.shape[0]}")
+    if len(set(sizes)) == 1:
+        if rank == src and full.shape[0] != world * sizes[0]:
+            raise ValueError(f"{full.shape[0]} stamps do not split evenly over {world} ranks: pass total=")
+        chunks = list(full.chunk(world)) if rank == src else None
+        dist.scatter(out, chunks, src=src)
+        return out
+    if rank == src:
+        off, reqs = 0, []
+        for r, n in enumerate(sizes):
+            part = full[off:off + n]
+            off += n
+            if r == src:
+                out.copy_(part)
+            elif n > 0:
+                reqs.append(dist.isend(part.contiguous(), dst=r))
+        for q in reqs:
+            q.wait()
+    elif out.shape[0] > 0:
+        dist.recv(out, src=src)
     return out
 
 
-def gather_stamps(local: torch.Tensor, dst: int = 0) -> Optional[torch.Tensor]:
+def gather_stamps(local: torch.Tensor, dst: int = 0, total: Optional[int] = None) -> Optional[torch.Tensor]:
+    """Inverse of scatter_stamps: rank `dst` returns the stamps of all ranks in rank order (None elsewhere)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local
-    bufs = [torch.empty_like(local) for _ in range(dist.get_world_size())] if dist.get_rank() == dst else None
-    dist.gather(local, bufs, dst=dst)
-    return torch.cat(bufs) if bufs is not None else None
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = _shard_sizes(total, world, int(local.shape[0]))
+    if len(set(sizes)) == 1:
+        bufs = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+        dist.gather(local, bufs, dst=dst)
+        return torch.cat(bufs) if bufs is not None else None
+    if rank == dst:
+        bufs = [torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) for n in sizes]
+        bufs[dst].copy_(local)
+        for r, n in enumerate(sizes):
+            if r != dst and n > 0:
+                dist.recv(bufs[r], src=r)
+        return torch.cat(bufs)
+    if local.shape[0] > 0:
+        dist.send(local.contiguous(), dst=dst)
+    return None

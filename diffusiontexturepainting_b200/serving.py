@@ -81,10 +81,19 @@ class StampBatcher:
     for its previous stamp before submitting the next one, which the request/response protocol already enforces.
     """
 
-    def __init__(self, generate: Callable[..., torch.Tensor], max_batch: int = 8, max_wait_ms: float = 2.0):
+    def __init__(self, generate: Callable[..., torch.Tensor], max_batch: int = 8, max_wait_ms: float = 2.0,
+                 brush_key: Optional[Callable[[], Hashable]] = None, lock=None):
+        """`lock`: the model's lock (TRTConditionalInpainter.lock); held across the brush check and the batched call.
+        `generate`: the model's bound `generate` (TRTConditionalInpainter.generate takes the model lock, so a
+        `set_brush` on the IOLoop thread cannot interleave with a batched call). `brush_key`: returns an id of the brush that
+        is current when a stamp is SUBMITTED (e.g. `lambda: model.brush_generation`): stamps submitted under different
+        brushes never share a batch, and a batch whose brush has been replaced before it runs fails instead of being
+        painted with the wrong texture."""
         if max_batch < 1:
             raise ValueError("max_batch must be >= 1")
         self._generate = generate
+        self._brush_key = brush_key
+        self._lock = lock if lock is not None else threading.RLock()
         self.max_batch = int(max_batch)
         self.max_wait = float(max_wait_ms) / 1e3
         self._pending: List[Tuple[Tuple, torch.Tensor, Dict[str, Any], Future]] = []
@@ -99,7 +108,7 @@ class StampBatcher:
         if c.dim() != 4 or c.shape[0] != 1 or c.shape[1] != 4 or c.shape[2] != c.shape[3]:
             raise ValueError(f"canvas must be (4,R,R) or (1,4,R,R), got {tuple(canvas.shape)}")
         fut: Future = Future()
-        key = (int(c.shape[-1]),) + _settings_key(settings)
+        key = (int(c.shape[-1]), self._brush_key() if self._brush_key else None) + _settings_key(settings)
         with self._cv:
             if self._closed:
                 raise RuntimeError("StampBatcher is closed")
@@ -147,8 +156,11 @@ class StampBatcher:
             if not live:
                 continue
             try:
-                canvases = torch.cat([r[1] for r in live], dim=0)
-                out = self._generate(canvases, **live[0][2])
+                with self._lock:
+                    if self._brush_key is not None and self._brush_key() != live[0][0][1]:
+                        raise RuntimeError("the brush changed between submission and execution of this stamp batch")
+                    canvases = torch.cat([r[1] for r in live], dim=0)
+                    out = self._generate(canvases, **live[0][2])
                 if out.shape[0] != len(live):
                     raise RuntimeError(f"model returned {out.shape[0]} stamps for a batch of {len(live)}")
                 self.batches.append(len(live))

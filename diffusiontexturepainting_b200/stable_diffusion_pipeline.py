@@ -89,19 +89,43 @@ class StableDiffusionPipeline:
             self.engine = None
 
 
-def load_state_dicts(cfg, lora_path=None, seed=20240726):
-    """Real checkpoints when present at the reference's paths (trt_model.py:48,58; models.py:796-813), else the seeded
-    synthetic inventory (this image has neither network nor weight files)."""
-    unet_sd, vae_sd, enc_sd = W.synth_model(cfg, seed)
+def synthetic_allowed() -> bool:
+    return os.environ.get("DTP_SYNTHETIC_WEIGHTS", "0") == "1"
+
+
+def load_state_dicts(cfg, lora_path=None, seed=20240726, synthetic=None):
+    """The four checkpoint components the reference loads — SD-1.5-inpaint UNet and VAE (models.py:796-813), the LoRA file
+    and image_encoder.pth (trt_model.py:48,58) — from the reference's paths. The reference crashes when one is absent; so
+    does this: a component that is missing raises CheckpointError unless seeded synthetic weights were asked for
+    explicitly (`synthetic=True` or DTP_SYNTHETIC_WEIGHTS=1: bench / tests / this image, which has neither network nor
+    weight files). In synthetic mode every substituted component is printed, and a real UNet never receives random LoRA
+    factors (the `up` factors of a missing LoRA file are zeroed, so the merge is a no-op)."""
+    from .checkpoints import CheckpointError, load_real_checkpoints
+    if synthetic is None:
+        synthetic = synthetic_allowed()
+    unet_sd, vae_sd, enc_sd = W.synth_model(cfg, seed)  # the inventory (keys and shapes), filled with seeded values
     if cfg.name != "sd15-inpaint":
-        return unet_sd, vae_sd, enc_sd
+        return unet_sd, vae_sd, enc_sd  # the narrow test configuration exists only with synthetic weights
     hf = os.environ.get("DTP_HF_DIR", "./HF_cache/stable-diffusion-inpainting")
-    from .checkpoints import load_real_checkpoints
+    enc_path = os.environ.get("DTP_IMAGE_ENCODER", "/workspace/checkpoints/image_encoder.pth")
     # a checkpoint file that exists must load completely (DTP_STRICT_WEIGHTS=0 downgrades that to a printed report)
     strict = os.environ.get("DTP_STRICT_WEIGHTS", "1") != "0"
-    reports = load_real_checkpoints(unet_sd, vae_sd, enc_sd, hf, lora_path,
-                                    os.environ.get("DTP_IMAGE_ENCODER", "/workspace/checkpoints/image_encoder.pth"),
-                                    strict=strict)
+    reports = load_real_checkpoints(unet_sd, vae_sd, enc_sd, hf, lora_path, enc_path, strict=strict)
     for r in reports:
         print("[dtp] " + r.summary())
+    have = {r.what.split(" <- ")[0] for r in reports}
+    missing = [c for c in ("unet", "vae", "lora", "image encoder") if c not in have]
+    if missing and not synthetic:
+        where = {"unet": os.path.join(hf, "unet"), "vae": os.path.join(hf, "vae"), "lora": str(lora_path),
+                 "image encoder": enc_path}
+        raise CheckpointError(
+            "checkpoint component(s) not found: " + ", ".join(f"{c} ({where[c]})" for c in missing) +
+            ". Set DTP_SYNTHETIC_WEIGHTS=1 to run on seeded random weights instead (benchmarks / tests only).")
+    if missing:
+        print("[dtp] WARNING: SYNTHETIC (seeded random) weights in use for: " + ", ".join(missing))
+        if "lora" in missing and "unet" in have:
+            for k in unet_sd:
+                if k.endswith("_lora.up.weight"):
+                    unet_sd[k] = torch.zeros_like(unet_sd[k])
+            print("[dtp] LoRA file absent next to a real UNet: LoRA factors zeroed (merge is a no-op)")
     return unet_sd, vae_sd, enc_sd

@@ -281,12 +281,12 @@ class UNet2DConditionTwin(nn.Module):
     def sinusoid(t, dim):
         # Timesteps(num_channels, flip_sin_to_cos=True, downscale_freq_shift=0)
         half = dim // 2
-        f = torch.exp(torch.arange(half, dtype=torch.float32) * (-math.log(10000.0) / half))
+        f = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device) * (-math.log(10000.0) / half))
         a = t[:, None].float() * f[None]
         return torch.cat([a.cos(), a.sin()], dim=-1)
 
     def forward(self, sample, timestep, ctx):
-        t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(sample.shape[0])
+        t = torch.as_tensor(timestep, dtype=torch.float32, device=sample.device).reshape(-1).expand(sample.shape[0])
         temb = self.time_embedding(self.sinusoid(t, self.cfg.block_out_channels[0]).to(sample.dtype))
         x = self.conv_in(sample)
         skips = [x]

@@ -8,6 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("DTP_SYNTHETIC_WEIGHTS", "1")  # profiling runs on the seeded synthetic inventory
 import torch  # noqa: E402
 
 from diffusiontexturepainting_b200 import weights as W  # noqa: E402

@@ -132,3 +132,32 @@ def test_absent_files_leave_the_inventory_untouched(tmp_path):
     assert ck.load_real_checkpoints(u0, v0, e0, str(tmp_path / "nowhere"), "/no/lora.bin", "/no/enc.pth") == []
     u1, _, _ = tiny(1)
     assert all(torch.equal(u0[k], u1[k]) for k in u1)
+
+
+def test_missing_checkpoints_raise_unless_synthetic_weights_are_requested(tmp_path, monkeypatch, capsys):
+    """the default server construction must not silently serve seeded random weights (the reference crashes in
+    from_pretrained / torch.load when a file is absent, models.py:796-813, trt_model.py:58)."""
+    from diffusiontexturepainting_b200 import weights as W
+    from diffusiontexturepainting_b200.checkpoints import CheckpointError
+    from diffusiontexturepainting_b200.stable_diffusion_pipeline import load_state_dicts
+    monkeypatch.setenv("DTP_HF_DIR", str(tmp_path / "nothing"))
+    monkeypatch.setenv("DTP_IMAGE_ENCODER", str(tmp_path / "none.pth"))
+    monkeypatch.delenv("DTP_SYNTHETIC_WEIGHTS", raising=False)
+    cfg = W.ModelConfig(unet=W.tiny_config().unet, vae=W.tiny_config().vae, enc=W.tiny_config().enc, name="sd15-inpaint")
+    with pytest.raises(CheckpointError, match="DTP_SYNTHETIC_WEIGHTS"):
+        load_state_dicts(cfg, str(tmp_path / "lora.bin"))
+    monkeypatch.setenv("DTP_SYNTHETIC_WEIGHTS", "1")
+    u, v, e = load_state_dicts(cfg, str(tmp_path / "lora.bin"))
+    assert "SYNTHETIC" in capsys.readouterr().out and len(u) and len(v) and len(e)
+    # a real UNet next to a missing LoRA file: the LoRA merge must be a no-op, not random
+    (tmp_path / "hf" / "unet").mkdir(parents=True)
+    real = {k: t for k, t in W.synth_state_dict(W.unet_param_shapes(cfg.unet), 99).items() if ".processor." not in k}
+    torch.save(real, tmp_path / "hf" / "unet" / "diffusion_pytorch_model.bin")
+    monkeypatch.setenv("DTP_HF_DIR", str(tmp_path / "hf"))
+    u, _, _ = load_state_dicts(cfg, str(tmp_path / "lora.bin"))
+    merged = W.merge_lora(u)
+    k = next(k for k in real if k.endswith("attn1.to_q.weight"))
+    assert torch.equal(merged[k], real[k])
+    # the narrow test configuration is synthetic by definition
+    monkeypatch.delenv("DTP_SYNTHETIC_WEIGHTS", raising=False)
+    assert len(load_state_dicts(W.tiny_config())[0])

@@ -48,6 +48,20 @@ def _worker(rank, world, port, ret):
     res = par.gather_stamps(mine[..., :3].contiguous() + 1, dst=0)
     if rank == 0:
         assert torch.equal(res, torch.arange(world * B * 64, dtype=torch.uint8).view(world * B, 4, 4, 4)[..., :3] + 1)
+    # uneven split: 5 stamps over 2 ranks -> 3 + 2 (shard_range), point to point, gathered back in order
+    n = 5
+    full = torch.arange(n * 8, dtype=torch.float32).view(n, 2, 4) if rank == 0 else None
+    lo, hi = par.shard_range(n, rank, world)
+    mine = par.scatter_stamps(full, (hi - lo, 2, 4), torch.float32, torch.device("cpu"), src=0, total=n)
+    assert torch.equal(mine, torch.arange(n * 8, dtype=torch.float32).view(n, 2, 4)[lo:hi])
+    back = par.gather_stamps(mine * 2, dst=0, total=n)
+    if rank == 0:
+        assert torch.equal(back, torch.arange(n * 8, dtype=torch.float32).view(n, 2, 4) * 2)
+        try:
+            par.scatter_stamps(torch.zeros(5, 1), (2, 1), torch.float32, torch.device("cpu"), src=0)
+            raise AssertionError("uneven split without total= must be refused")
+        except ValueError:
+            pass
         ret.put("ok")
     dist.barrier()
     dist.destroy_process_group()

@@ -239,6 +239,17 @@ def test_flash_attention(seq, heads, d, batch):
                                              (3, 4096, 320, 0, 1), (3, 4096, 640, 320, 1), (2, 1024, 1280, 640, 0),
                                              (2, 16384, 128, 0, 1)])
 def test_groupnorm(n, hw, c0, c1, silu):
+    _groupnorm_case(n, hw, c0, c1, silu)
+
+
+@pytest.mark.parametrize("n,hw,c,silu", [(1, 262144, 128, 1), (2, 262144, 128, 1), (1, 262144, 256, 1), (2, 65536, 256, 1),
+                                         (2, 16384, 512, 0), (3, 4096, 320, 1), (12, 1024, 320, 1)])
+def test_groupnorm_vae_scale(n, hw, c, silu):
+    """VAE GroupNorms of the 512 x 512 stamp: rows = n * hw = 262 144 / 524 288 (C2), plus the C3-per-GPU UNet shape."""
+    _groupnorm_case(n, hw, c, 0, silu)
+
+
+def _groupnorm_case(n, hw, c0, c1, silu):
     L = nat.lib()
     x0 = h(rnd(n, hw, c0) * 2 + 0.5)
     x1 = h(rnd(n, hw, c1, seed=2)) if c1 else None
@@ -341,12 +352,14 @@ def test_ddim_step_bit_exact():
     assert torch.equal(out.cpu(), ref)
 
 
-def test_canvas_preprocess_and_composite():
+@pytest.mark.parametrize("B,R,pad", [(2, 64, 21), (1, 256, 150), (2, 512, 150), (1, 512, 255), (1, 128, 1), (1, 64, 200)])
+def test_canvas_preprocess_and_composite(B, R, pad):
+    """pad = 150 at 256 / 512 is the server operating point (manager.py:104-110); 255 is the wire maximum (uint8 header
+    field, server_io.py:105-119); pad > R covers windows wider than the image."""
     L = nat.lib()
-    B, R, pad = 2, 64, 21
     canvas = torch.rand(B, 4, R, R, generator=torch.Generator().manual_seed(1))
     canvas[:, 3] = (canvas[:, 3] > 0.97).float()
-    canvas[1, 3, :20] = 1.0
+    canvas[B - 1, 3, :20] = 1.0
     brush = torch.rand(1, 3, R, R, generator=torch.Generator().manual_seed(2))
     cd, bd = canvas.to(DEV), brush.to(DEV)
     mi, m, ci, cm = (torch.empty(B, c, R, R, device=DEV) for c in (3, 1, 3, 1))
@@ -358,7 +371,9 @@ def test_canvas_preprocess_and_composite():
     masks = canvas[:, 3:]
     masked = images * masks
     lo, hi = pad // 2, pad - pad // 2 - 1
-    dil = F.max_pool2d(F.pad(masks, (lo, hi, lo, hi), value=-1e4), pad, stride=1)
+    # flat window maximum == row maximum of column maxima (exact), evaluated on the device to keep pad = 150 @ 512 fast
+    dil = F.max_pool2d(F.pad(masks.to(DEV), (lo, hi, 0, 0), value=-1e4), (1, pad), stride=1)
+    dil = F.max_pool2d(F.pad(dil, (0, 0, lo, hi), value=-1e4), (pad, 1), stride=1).cpu()
     hint = 1 - dil
     ctx_img = masked + (brush * 2 - 1) * hint
     ctx_mask = torch.clamp(masks + hint, min=0, max=1)

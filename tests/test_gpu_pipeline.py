@@ -2,7 +2,10 @@
 PyTorch restatement of the reference pipeline — on identical seeded inputs and fp16-representable weights.
 
 Tolerances (SURVEY.md §8c): UNet single forward rel-L2 <= 1e-2; VAE encode / decode <= 1e-2; image encoder <= 1e-2;
-end-to-end stamp: PSNR >= 35 dB against the fp32 oracle and >= 99 % of pixels within 2/255 ... stated per test."""
+end-to-end stamp (SURVEY.md §8c as written): PSNR >= 40 dB on generate_raw (BEFORE the alpha composite) and >= 99.9 % of the
+pixels within 2/255 against the fp32 oracle; uint8 wire output <= 2 LSB on >= 99.9 % of the bytes. The benchmarked
+configurations are covered at full model size: C2 (512 x 512, steps = 20 -> 19 evaluations, and the strict 20) and C3 per
+GPU (256 x 256, B = 4, 10 evaluations)."""
 import json
 import math
 import os
@@ -102,7 +105,7 @@ def check_vae(b, R, B=2, name="tiny"):
     assert e < 1e-2
 
 
-def check_unet(b, R, B=1, name="tiny"):
+def check_unet(b, R, B=1, name="tiny", n_steps=4, steps=(0, 3)):
     from oracle import unet as un
     from oracle.ddim import DDIM
     h = R // 8
@@ -111,11 +114,11 @@ def check_unet(b, R, B=1, name="tiny"):
     unc = torch.randn(1, 14, b.cfg.unet.cross_dim, generator=gen(9)).to(DEV)
     b.engine.set_condition(emb[0], unc[0])
     d = DDIM()
-    d.set_timesteps(4)
+    d.set_timesteps(n_steps)
     ts = [float(t) for t in d.timesteps]
-    b.engine.set_schedule(ts, [0.5] * 4, [0.6] * 4, 2.0, 1.0, 4)
+    b.engine.set_schedule(ts, [0.5] * n_steps, [0.6] * n_steps, 2.0, 1.0, n_steps)
     ctx = torch.cat([unc.expand(B, -1, -1), emb.expand(B, -1, -1), emb.expand(B, -1, -1)]).half().float()
-    for step in (0, 3):
+    for step in steps:
         got = b.engine.unet_forward(sample, step)
         ref = un.unet_forward(b.oracle_sds[0], b.cfg.unet, sample.half().float(), ts[step], ctx)
         e = rel_l2(got, ref)
@@ -133,10 +136,13 @@ def check_encoder(b, name):
     assert e < 1e-2
 
 
-def check_e2e(b, R, steps, B=1, name="tiny", psnr_min=35.0):
+def check_e2e(b, R, steps, B=1, name="tiny", psnr_min=40.0, frac_min=0.999, strict=False, pad=None, u8=True):
+    """generate_raw (before the composite, where every pixel is generated) against the fp32 oracle: PSNR and the fraction
+    of pixels within 2/255; then the composited float output and the uint8 wire output (handler.py:55-56 truncation)."""
     from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
     model = TRTConditionalInpainter(R, device=0, model_config=b.cfg, state_dicts=b.sds, max_batch_size=B)
     model.pipeline.sample_posterior = False
+    model.pipeline.strict_schedule = strict
     brush = smooth_image(1, 3, R + 16)
     model.set_brush(brush)
     ora = b.oracle(R)
@@ -144,18 +150,41 @@ def check_e2e(b, R, steps, B=1, name="tiny", psnr_min=35.0):
     e_emb = rel_l2(model.conditioning[0], ora.conditioning[0])
     canvas = make_canvas(B, R)
     lat = torch.randn(B, 4, R // 8, R // 8, generator=gen(42))
-    settings = dict(steps=steps, context_pad=R // 2, tg_steps=steps, width=R, cfg_weight=2.0, tg_weight=1.0)
-    got = model.generate(canvas, init_latents=lat, **settings).cpu()
-    ref = ora.generate(canvas, lat.to(DEV), **settings).cpu()
-    mse = ((got - ref) ** 2).mean().item()
+    settings = dict(steps=steps, context_pad=pad if pad is not None else R // 2, tg_steps=steps, width=R, cfg_weight=2.0,
+                    tg_weight=1.0)
+    with torch.inference_mode():
+        ref_raw = ora.generate_raw(canvas, lat.to(DEV), strict=strict, **settings).cpu()
+    got_raw = model.generate_raw(canvas, init_latents=lat, **settings).cpu()
+    mse = ((got_raw - ref_raw) ** 2).mean().item()
     psnr = 10 * math.log10(1.0 / max(mse, 1e-20))
-    frac = ((got - ref).abs() <= 2.0 / 255).float().mean().item()
-    log(f"{name}.e2e.R{R}.S{steps}.B{B}", psnr=psnr, frac_within_2_255=frac, emb_rel_l2=e_emb,
-        launches=model.engine.counter("launches"))
-    assert torch.isfinite(got).all()
+    frac = ((got_raw - ref_raw).abs() <= 2.0 / 255).float().mean().item()
+    got = model.generate(canvas, init_latents=lat, **settings).cpu()
+    alpha = canvas[:, 3:]
+    ref = canvas[:, :3] * alpha + ref_raw * (1 - alpha)
+    comp_max = (got - ref).abs().max().item()
+    n_eval = steps if strict else steps - 1
+    tag = f"{name}.e2e.R{R}.S{steps}{'strict' if strict else ''}.B{B}"
+    rec = dict(psnr_raw=psnr, frac_within_2_255_raw=frac, emb_rel_l2=e_emb, unet_evaluations=n_eval,
+               composite_max_abs=comp_max, launches=model.engine.counter("launches"))
+    if u8:
+        canvas_u8 = (canvas.permute(0, 2, 3, 1) * 255).to(torch.uint8)
+        out_u8 = model.stamp_u8(canvas_u8, init_latents=lat, **settings).cpu()
+        cq = canvas_u8.permute(0, 3, 1, 2).float() / 255
+        with torch.inference_mode():
+            ref_q = ora.generate(cq, lat.to(DEV), strict=strict, **settings).cpu()
+        ref_u8 = (ref_q * 255).to(torch.uint8).permute(0, 2, 3, 1)
+        d8 = (out_u8.int() - ref_u8.int()).abs()
+        rec.update(u8_max_lsb=int(d8.max()), u8_frac_within_2=(d8 <= 2).float().mean().item())
+    log(tag, **rec)
+    assert torch.isfinite(got_raw).all() and torch.isfinite(got).all()
     assert e_emb < 1e-2
-    assert psnr >= psnr_min
+    assert psnr >= psnr_min, rec
+    assert frac >= frac_min, rec
+    if u8:
+        assert rec["u8_frac_within_2"] >= frac_min, rec
     model.pipeline.teardown()
+    del model
+    torch.cuda.empty_cache()
     return got, ref
 
 
@@ -192,7 +221,41 @@ def test_full_encoder(full):
 
 
 def test_full_e2e(full):
-    check_e2e(full, 128, 5, name="sd15", psnr_min=30.0)
+    check_e2e(full, 128, 5, name="sd15")
+
+
+# ---- the benchmarked configurations at full model size (BASELINE.json configs 2 and 3; inpaint_pipeline.py:52-153) ----
+def test_full_unet_c2_512(full):
+    """one UNet evaluation at 512 x 512 / B = 1 (12 288 rows at level 0): first and last entry of a 20-entry schedule; this
+    is where the measured tile table (320-wide pair tiles, in-kernel split-K) is exercised"""
+    check_unet(full, 512, name="sd15", n_steps=20, steps=(0, 19))
+
+
+def test_full_unet_c3_256_b4(full):
+    check_unet(full, 256, B=4, name="sd15", n_steps=10, steps=(0, 9))
+
+
+def test_full_vae_c2_512(full):
+    check_vae(full, 512, B=2, name="sd15")
+
+
+def test_full_vae_c3_256(full):
+    check_vae(full, 256, B=2, name="sd15")
+
+
+def test_full_e2e_c2_reference_semantics(full):
+    """512 x 512, steps = 20 through the facade = 19 evaluations (t_start = 1), context_pad 150: the server's call"""
+    check_e2e(full, 512, 20, name="sd15", pad=150)
+
+
+def test_full_e2e_c2_strict(full):
+    """512 x 512, all 20 evaluations: the configuration bench.py times"""
+    check_e2e(full, 512, 20, name="sd15", strict=True, pad=150, u8=False)
+
+
+def test_full_e2e_c3_per_gpu(full):
+    """256 x 256, B = 4 stamps, 10 evaluations (strict): the per-GPU share of BASELINE config 3"""
+    check_e2e(full, 256, 10, B=4, name="sd15", strict=True, pad=150)
 
 
 def test_graph_replay_and_options_are_equivalent(tiny):

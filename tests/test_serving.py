@@ -58,6 +58,7 @@ def test_set_brush_uses_the_cache_without_touching_the_encoder():
     m.image_encoder, m.pipeline, m._resolution = Enc(), Pipe(), 32
     m.brush_cache = BrushCache(2)
     m.conditioning = m.image = None
+    m.lock, m.brush_generation = threading.RLock(), 0
     b1, b2 = torch.rand(3, 48, 64), torch.rand(3, 64, 48)
     m.set_brush(b1)
     e1 = m.conditioning[0].clone()
@@ -65,7 +66,7 @@ def test_set_brush_uses_the_cache_without_touching_the_encoder():
     m.set_brush(b1)
     assert calls == {"encode": 2, "cond": 3}
     assert torch.equal(m.conditioning[0], e1) and torch.equal(m.pipeline.last, e1)
-    assert m.image.shape == (1, 3, 32, 32)
+    assert m.image.shape == (1, 3, 32, 32) and m.brush_generation == 3
     m.brush_cache = None              # cache disabled: every switch re-encodes
     m.set_brush(b1)
     assert calls["encode"] == 3
@@ -130,3 +131,22 @@ def test_batcher_rejects_malformed_canvases():
         for bad in (torch.zeros(3, 8, 8), torch.zeros(2, 4, 8, 8), torch.zeros(4, 8, 9)):
             with pytest.raises(ValueError):
                 b.submit(bad, SETTINGS)
+
+
+def test_batcher_keeps_brushes_apart_and_fails_a_batch_whose_brush_was_replaced():
+    """stamps submitted under different brushes must not be coalesced, and a batch must not be painted with a
+    brush that replaced the one it was submitted under."""
+    model = FakeModel(delay=0.05)
+    gen = {"v": 0}
+    lock = threading.RLock()
+    with StampBatcher(model.generate, max_batch=8, max_wait_ms=30, brush_key=lambda: gen["v"], lock=lock) as b:
+        f0 = b.submit(torch.zeros(4, 8, 8), SETTINGS)
+        f0.result(timeout=5)
+        f1 = b.submit(torch.zeros(4, 8, 8), SETTINGS)   # submitted under brush 0 ...
+        with lock:
+            gen["v"] = 1                                  # ... which is replaced before the batch runs
+        f2 = b.submit(torch.ones(4, 8, 8), SETTINGS)     # submitted under brush 1
+        with pytest.raises(RuntimeError, match="brush changed"):
+            f1.result(timeout=5)
+        assert torch.all(f2.result(timeout=5) == 1.0)
+    assert [n for n, _, _ in model.calls] == [1, 1]      # f1 never reached the model, f2 ran alone
