@@ -73,9 +73,48 @@ __device__ __forceinline__ void store_f32_chunk(float* out, const float (&v)[32]
     }
 }
 
-// bias_chunk: 32 floats for columns col0.. (shared memory in the main kernel, global in the finalize kernel), or nullptr
+// folded LayerNorm: (rstd, -rstd * mean) of A row `grow` from the producer's per-chunk partial sums (gemm_tc.h)
+__device__ __forceinline__ void ln_row_coef(const GemmParams& p, long long grow, float& ln_r, float& ln_nm) {
+    const float2* sp = p.ln_stats + grow;
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    int ch = 0;
+    for (; ch + 4 <= p.ln_chunks; ch += 4) {  // four independent loads in flight
+        const float2 a = __ldcg(sp + static_cast<long long>(ch) * p.ln_rows);
+        const float2 b = __ldcg(sp + static_cast<long long>(ch + 1) * p.ln_rows);
+        const float2 c = __ldcg(sp + static_cast<long long>(ch + 2) * p.ln_rows);
+        const float2 d = __ldcg(sp + static_cast<long long>(ch + 3) * p.ln_rows);
+        s0 += a.x + b.x;
+        s1 += c.x + d.x;
+        q0 += a.y + b.y;
+        q1 += c.y + d.y;
+    }
+    for (; ch < p.ln_chunks; ++ch) {
+        const float2 a = __ldcg(sp + static_cast<long long>(ch) * p.ln_rows);
+        s0 += a.x;
+        q0 += a.y;
+    }
+    const float mean = (s0 + s1) * p.ln_inv_c;
+    const float var = fmaxf((q0 + q1) * p.ln_inv_c - mean * mean, 0.0f);
+    ln_r = rsqrtf(var + p.ln_eps);
+    ln_nm = -ln_r * mean;
+}
+// (sum, sum of squares) of the 32 values as they are stored (fp16-rounded), for a following folded LayerNorm
+__device__ __forceinline__ void emit_row_stats(const GemmParams& p, long long grow, int col0, const float (&v)[32]) {
+    float s = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float x = __half2float(__float2half_rn(v[i]));
+        s += x;
+        q = fmaf(x, x, q);
+    }
+    p.stats_out[static_cast<long long>(col0 >> 5) * p.stats_rows + grow] = make_float2(s, q);
+}
+
+// bias_chunk: 32 floats for columns col0.. (shared memory in the main kernel, global in the finalize kernel), or nullptr.
+// grow: row index in the statistics buffers ((z2 * nz1 + z1) * M + row); colsum_chunk: like bias_chunk, for the folded LayerNorm
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long out_off, long long res_off, int row,
-                                                 int col0, float (&v)[32], const float* bias_chunk) {
+                                                 int col0, float (&v)[32], const float* bias_chunk,
+                                                 long long grow = 0, const float* colsum_chunk = nullptr) {
     const int N = p.N;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
@@ -100,7 +139,13 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
             for (int i = 0; i < 4; ++i) rraw[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
         }
     }
-    if (flags & EPI_BIAS_M) {
+    if (p.ln_stats != nullptr) {
+        float ln_r, ln_nm;
+        ln_row_coef(p, grow, ln_r, ln_nm);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            v[i] = fmaf(v[i], ln_r, fmaf(ln_nm, colsum_chunk[i], bias_chunk != nullptr ? bias_chunk[i] : 0.0f));
+    } else if (flags & EPI_BIAS_M) {
         const float rb = p.bias ? __ldg(p.bias + row) : 0.0f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, rb);
@@ -208,6 +253,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     }
     __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
     store_half_chunk(out, v, ncols, (p.ldc & 7) == 0 && (out_off & 7) == 0);
+    if (p.stats_out != nullptr) emit_row_stats(p, grow, col0, v);
 }
 
 // bounded mbarrier wait: a descriptor / byte-count bug must trap, not hang the GPU
@@ -337,6 +383,7 @@ __global__ void __launch_bounds__(320, OCC)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full_bar + STAGES);
     int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);  // split-K arrival ticket of the current tile (epilogue warps)
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);  // [BN]
+    float* scolsum = sbias + BN;                              // [BN] folded LayerNorm: row sums of the scaled weights
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -547,6 +594,7 @@ __global__ void __launch_bounds__(320, OCC)
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
+        const bool ln_on = p.ln_stats != nullptr;
         const bool fused_reduce = p.splits > 1 && p.tile_counters != nullptr;
         // 32-byte aligned full-width fp16 rows (st.global.v8 / 16-byte residual loads) and an epilogue the fast path covers
         const bool fast_epi =
@@ -564,9 +612,15 @@ __global__ void __launch_bounds__(320, OCC)
             const int row = tile_row(p, c, r);
             const long long out_off = static_cast<long long>(c.z1) * p.out_zs1 + static_cast<long long>(c.z2) * p.out_zs2;
             const long long res_off = static_cast<long long>(c.z1) * p.res_zs1 + static_cast<long long>(c.z2) * p.res_zs2;
-            if (col_bias) {
+            // row index in the statistics buffers of a folded LayerNorm (batch entries are blocks of M rows in z order)
+            const long long grow = static_cast<long long>(c.z2 * p.nz1 + c.z1) * p.M + (row >= 0 ? row : 0);
+            if (col_bias || ln_on) {
                 epi_bar_sync();  // previous tile's readers are done with sbias
-                for (int i = et; i < BN; i += 256) sbias[i] = (c.n0 + i < p.N) ? __ldg(p.bias + c.n0 + i) : 0.0f;
+                const long long boff = static_cast<long long>(c.z1) * p.bias_zs1 + c.n0;
+                for (int i = et; i < BN; i += 256) {
+                    sbias[i] = (col_bias && c.n0 + i < p.N) ? __ldg(p.bias + boff + i) : 0.0f;
+                    if (ln_on) scolsum[i] = (c.n0 + i < p.N) ? __ldg(p.ln_colsum + boff + i) : 0.0f;
+                }
                 epi_bar_sync();
             }
             // chunks this warp owns: cc = 32*half, 32*half + 64, ... (bounded by the tile width and by N)
@@ -591,6 +645,8 @@ __global__ void __launch_bounds__(320, OCC)
                         rres[it][i] = (rrow != nullptr && it < n_mine) ? __ldg(reinterpret_cast<const uint4*>(rrow + 64 * it) + i)
                                                                        : make_uint4(0u, 0u, 0u, 0u);
                 }
+                float ln_r = 1.0f, ln_nm = 0.0f;
+                if (ln_on && row >= 0) ln_row_coef(p, grow, ln_r, ln_nm);  // L2 latency hides behind the mainloop
                 mbar_wait_bounded(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (wave == 0 && et == 0) DBG_MARK(4);
@@ -611,7 +667,11 @@ __global__ void __launch_bounds__(320, OCC)
                         if (RB == 1 && it + 1 < IT && it + 1 < n_mine)
                             tmem_ld_32x32(tmem_acc + static_cast<uint32_t>(cc + 64), raw[0]);
                         const float* bc = sbias + cc;
-                        if (col_bias) {
+                        if (ln_on) {
+                            const float* cs = scolsum + cc;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], ln_r, fmaf(ln_nm, cs[i], bc[i]));
+                        } else if (col_bias) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.alpha, bc[i]);
                         } else {
@@ -645,6 +705,7 @@ __global__ void __launch_bounds__(320, OCC)
                                             rres[it % RD][i] = __ldg(reinterpret_cast<const uint4*>(rrow + 64 * (it + RD)) + i);
                                     }
                                 }
+                                if (p.stats_out != nullptr) emit_row_stats(p, grow, c.n0 + cc, v);
                                 __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc +
                                               c.n0 + cc;
 #pragma unroll
@@ -730,7 +791,8 @@ __global__ void __launch_bounds__(320, OCC)
                         const int ncols = min(32, p.N - (c.n0 + cc));
                         store_f32_chunk(ws, v, ncols, (p.N & 3) == 0);
                     } else {
-                        epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr);
+                        epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr, grow,
+                                         scolsum + cc);
                     }
                 }
             }
@@ -811,7 +873,8 @@ __global__ void __launch_bounds__(320, OCC)
                         v[4 * j + 2] = t4.z;
                         v[4 * j + 3] = t4.w;
                     }
-                    epilogue_store32(p, out_off, res_off, orow, col0, v, col_bias ? sbias + ch * 32 : nullptr);
+                    epilogue_store32(p, out_off, res_off, orow, col0, v, col_bias ? sbias + ch * 32 : nullptr,
+                                     static_cast<long long>(c.z2 * p.nz1 + c.z1) * p.M + orow, scolsum + ch * 32);
                 }
             }
             if (++acc == NACC) {
@@ -875,16 +938,21 @@ __global__ void __launch_bounds__(256) gemm_splitk_finalize_kernel(const __grid_
                 if (i < ncols) v[i] += ws[i];
         }
     }
-    float b[32];
+    float b[32], cs[32];
     const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
+    const int z1 = zb % p.nz1, z2 = zb / p.nz1;
+    const long long boff = static_cast<long long>(z1) * p.bias_zs1 + col0;
     if (col_bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(p.bias + col0 + i) : 0.0f;
+        for (int i = 0; i < 32; ++i) b[i] = (i < ncols) ? __ldg(p.bias + boff + i) : 0.0f;
     }
-    const int z1 = zb % p.nz1, z2 = zb / p.nz1;
+    if (p.ln_stats != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cs[i] = (i < ncols) ? __ldg(p.ln_colsum + boff + i) : 0.0f;
+    }
     const long long out_off = static_cast<long long>(z1) * p.out_zs1 + static_cast<long long>(z2) * p.out_zs2;
     const long long res_off = static_cast<long long>(z1) * p.res_zs1 + static_cast<long long>(z2) * p.res_zs2;
-    epilogue_store32(p, out_off, res_off, row, col0, v, col_bias ? b : nullptr);
+    epilogue_store32(p, out_off, res_off, row, col0, v, col_bias ? b : nullptr, static_cast<long long>(zb) * p.M + row, cs);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1324,7 +1392,7 @@ struct PerDeviceFlag {
 
 template <int BN, int STAGES>
 static int launch_light(const GemmOp* op, cudaStream_t stream) {
-    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
+    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 8 + 1024;
     static_assert(SMEM <= 113 * 1024 && 2 * BN <= 256, "two CTAs per SM");
     static PerDeviceFlag attr_flag;
     bool& attr_set = attr_flag.here();
@@ -1359,8 +1427,8 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
 
 template <int BN, int STAGES, int STAGES2>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
-    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 4 + 1024;
-    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
+    constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 8 + 1024;
+    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 8 + 1024;
     static_assert(SMEM <= 227 * 1024 && SMEM2 <= 227 * 1024, "shared memory budget");
     static PerDeviceFlag attr_flag;
     bool& attr_set = attr_flag.here();
@@ -1430,7 +1498,7 @@ static int max_pair_clusters() {
     int local = -1;
     int& n = kc ? kc->max_pair_clusters : local;
     if (n < 0) {
-        constexpr int SMEM2 = 8 * (128 * 128 + 128 * 64) + (3 * 8 + 4) * 8 + 16 + 128 * 4 + 1024;
+        constexpr int SMEM2 = 8 * (128 * 128 + 128 * 64) + (3 * 8 + 4) * 8 + 16 + 128 * 8 + 1024;
         cudaFuncSetAttribute(gemm_tc_kernel<128, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * (num_sms() / 2));
@@ -1456,7 +1524,7 @@ static int max_pair_clusters() {
 // BN = 320: CTA pairs only (a single-CTA 128 x 320 tile would need 56 KB per stage)
 template <int BN, int STAGES2>
 static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
-    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 4 + 1024;
+    constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 8 + 1024;
     static_assert(SMEM2 <= 227 * 1024, "shared memory budget");
     static PerDeviceFlag attr_flag;
     bool& attr_set = attr_flag.here();

@@ -74,6 +74,19 @@ struct GemmParams {
                        // the op's mapBL (n_last rows; pair mode n_last / 2), so a narrow tail tile costs what it computes
     int dbg_mode;      // tuning aid (DTP_EPI_DEBUG): 1 = skip global stores, 2 = skip TMEM loads
     int* err_flag;     // mapped host flag of the owning KernelCtx: set when a cross-CTA wait gives up (kctx.h)
+    // ---- LayerNorm folded into the contraction (trt_inference/models.py:304-365 fuses LN as one plugin op in front of the
+    // GEMM; here it disappears into it): with W' = W diag(gamma) the normalised product is
+    //     LN(x) W^T = rstd_r * (x W'^T - mean_r * colsum(W')) + W beta,
+    // so the kernel multiplies the RAW rows and the epilogue applies out = rstd_r * (acc - mean_r * ln_colsum[n]) + bias[n].
+    // Row statistics arrive as per-(32-column chunk, row) partial (sum, sum of squares) written by the producer of x.
+    const float2* ln_stats;   // [ln_chunks][ln_rows], row index = (z2 * nz1 + z1) * M + row; nullptr = no folded LayerNorm
+    const float* ln_colsum;   // [N] (+ z1 * bias_zs1): row sums of the fp16 gamma-scaled weights
+    int ln_chunks, ln_rows;
+    float ln_inv_c, ln_eps;
+    // ---- row statistics of THIS op's fp16 output for a following folded LayerNorm: one float2 per (32-column chunk, row)
+    float2* stats_out;        // [N / 32][stats_rows]; needs N % 32 == 0 and a plain fp16 row-major output
+    int stats_rows;
+    long long bias_zs1;       // bias / ln_colsum offset (elements) per batch coordinate z1 (folded cross-attention scores)
 };
 
 struct GemmOp {

@@ -703,6 +703,69 @@ int launch_layernorm(const __half* x, int rows, int C, const float* gamma, const
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// folded LayerNorm: weight preparation (load time / per brush)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_fold_weights_kernel(const __half* __restrict__ W, int N, int K, int ldw,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ bias_in, __half* __restrict__ Wout,
+                                                             float* __restrict__ colsum, float* __restrict__ bias_out) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float cs = 0.0f, bs = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = __half2float(W[static_cast<long long>(n) * ldw + k]);
+        const __half wp = __float2half_rn(w * __ldg(gamma + k));
+        Wout[static_cast<long long>(n) * ldw + k] = wp;
+        cs += __half2float(wp);
+        bs = fmaf(w, __ldg(beta + k), bs);
+    }
+    cs = warp_sum(cs);
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        if (colsum) colsum[n] = cs;
+        if (bias_out) bias_out[n] = bs + (bias_in ? bias_in[n] : 0.0f);
+    }
+}
+
+int launch_ln_fold_weights(const __half* W, int N, int K, int ldw, const float* gamma, const float* beta,
+                           const float* bias_in, __half* Wout, float* colsum, float* bias_out, cudaStream_t st) {
+    ln_fold_weights_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, N, K, ldw, gamma, beta, bias_in, Wout, colsum, bias_out);
+    return check_launch("ln_fold_weights");
+}
+
+// grid (heads * 16, 3): one warp per score row
+__global__ void __launch_bounds__(32) cross_ln_finish_kernel(const __half* __restrict__ wscore, const __half* __restrict__ kv,
+                                                            const float* __restrict__ qbeta, int C, int heads, int T,
+                                                            float scale, float* __restrict__ colsum,
+                                                            float* __restrict__ bias) {
+    pdl_enter();
+    const int n = blockIdx.x, slot = blockIdx.y, lane = threadIdx.x;
+    const int HP = heads * 16, h = n >> 4, j = n & 15, d = C / heads;
+    const __half* w = wscore + (static_cast<long long>(slot) * HP + n) * C;
+    float cs = 0.0f;
+    for (int c = lane; c < C; c += 32) cs += __half2float(w[c]);
+    cs = warp_sum(cs);
+    float bs = 0.0f;
+    if (j < T) {
+        const int ctx = slot == 0 ? 0 : 1;  // [uncond | cond | cond] (inpaint_pipeline.py:140)
+        const __half* k = kv + (static_cast<long long>(ctx) * T + j) * 2 * C + h * d;
+        for (int i = lane; i < d; i += 32) bs = fmaf(__half2float(k[i]), __ldg(qbeta + h * d + i), bs);
+    }
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        colsum[slot * HP + n] = cs;
+        bias[slot * HP + n] = scale * bs;
+    }
+}
+
+int launch_cross_ln_finish(const __half* wscore, const __half* kv, const float* qbeta, int C, int heads, int T,
+                           float scale, float* colsum, float* bias, cudaStream_t st) {
+    launch_k(cross_ln_finish_kernel, dim3(heads * 16, 3), dim3(32), 0, st, wscore, kv, qbeta, C, heads, T, scale, colsum, bias);
+    return check_launch("cross_ln_finish");
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // row softmax, in place
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, long long rows, int cols, int ld) {

@@ -76,6 +76,16 @@ int launch_canvas_preprocess(const float* canvas, const float* brush, int B, int
 int launch_composite(const float* canvas, const float* raw, int B, int R, float* out_f32, unsigned char* out_u8hwc,
                      cudaStream_t st);
 
+// Folded LayerNorm (gemm_tc.h): W'[n,k] = fp16(W[n,k] * gamma[k]); colsum[n] = sum_k W'[n,k]; bias_out[n] = bias_in[n] (or 0)
+// + sum_k W[n,k] * beta[k]. One warp per weight row; load time only.
+int launch_ln_fold_weights(const __half* W, int N, int K, int ldw, const float* gamma, const float* beta,
+                           const float* bias_in, __half* Wout, float* colsum, float* bias_out, cudaStream_t st);
+// Folded cross-attention scores with a folded LayerNorm, per brush: for every row n = h * 16 + j of the (3, heads * 16, C)
+// score operand: colsum[slot][n] = sum_c Wscore[slot][n][c]; bias[slot][n] = scale * K_slot[j, head h] . qbeta[head h]
+// (qbeta = Wq beta, the LayerNorm shift seen through the query projection); rows of the pad tokens j >= T give 0.
+int launch_cross_ln_finish(const __half* wscore, const __half* kv, const float* qbeta, int C, int heads, int T,
+                           float scale, float* colsum, float* bias, cudaStream_t st);
+
 // misc small helpers used by the runtime
 int launch_add_rows_bcast(__half* x, const float* add, long long rows, int C, int period, cudaStream_t st);  // x[r,:] += add[r % period,:]
 int launch_f32_to_f16(const float* x, __half* out, long long n, cudaStream_t st);

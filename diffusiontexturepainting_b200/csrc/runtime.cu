@@ -137,6 +137,11 @@ struct Lin {
     int flags = 0;
     float alpha = 1.0f;
     int hw_out = 0;
+    // folded LayerNorm on the A rows (gemm_tc.h) / row statistics of the output for the next folded LayerNorm
+    const float2* ln_stats = nullptr;
+    const float* ln_colsum = nullptr;
+    int ln_C = 0;
+    float2* stats_out = nullptr;
 };
 
 struct Builder {
@@ -241,6 +246,18 @@ struct Builder {
         op.p.flags |= a.flags;
         op.p.alpha = a.alpha;
         op.p.hw_out = a.hw_out;
+        if (a.ln_stats) {
+            op.p.ln_stats = a.ln_stats;
+            op.p.ln_colsum = a.ln_colsum;
+            op.p.ln_chunks = a.ln_C / 32;
+            op.p.ln_rows = static_cast<int>(a.M);
+            op.p.ln_inv_c = 1.0f / static_cast<float>(a.ln_C);
+            op.p.ln_eps = 1e-5f;
+        }
+        if (a.stats_out) {
+            op.p.stats_out = a.stats_out;
+            op.p.stats_rows = static_cast<int>(a.M);
+        }
         push_gemm(op);
     }
 
@@ -264,6 +281,11 @@ struct Builder {
         float alpha = 1.0f;
         int aux = 0;
         const char* label = "bmm";
+        const float2* ln_stats = nullptr;  // folded LayerNorm (rows of all batch entries: nz1 * M)
+        const float* ln_colsum = nullptr;
+        int ln_C = 0;
+        long long bias_zs1 = 0;
+        float2* stats_out = nullptr;
     };
     void bmm(const Bmm& a) {
         if (!ok) return;
@@ -287,6 +309,19 @@ struct Builder {
         op.p.flags |= a.flags;
         op.p.alpha = a.alpha;
         op.p.aux = a.aux;
+        op.p.bias_zs1 = a.bias_zs1;
+        if (a.ln_stats) {
+            op.p.ln_stats = a.ln_stats;
+            op.p.ln_colsum = a.ln_colsum;
+            op.p.ln_chunks = a.ln_C / 32;
+            op.p.ln_rows = a.M * a.nz1 * a.nz2;
+            op.p.ln_inv_c = 1.0f / static_cast<float>(a.ln_C);
+            op.p.ln_eps = 1e-5f;
+        }
+        if (a.stats_out) {
+            op.p.stats_out = a.stats_out;
+            op.p.stats_rows = a.M * a.nz1 * a.nz2;
+        }
         push_gemm(op, a.label);
     }
 
@@ -817,7 +852,54 @@ int Engine::finalize_weights() {
     cond_plan_.clear();
     temb_dirty_ = true;
     cond_set_ = false;
+    if (prepare_ln_fold()) return -1;
     finalized_ = true;
+    return 0;
+}
+
+// gamma-scaled copies of the weights behind the three LayerNorms of every transformer block, their row sums and W beta
+int Engine::prepare_ln_fold() {
+    ln_.clear();
+    std::vector<LnFold> v(tf_names_.size());
+    const int heads = cfg_.unet_heads, HP = heads * 16;
+    for (size_t i = 0; i < tf_names_.size(); ++i) {
+        const std::string t = "unet." + tf_names_[i] + ".transformer_blocks.0";
+        const WT* qkv = find(t + ".attn1.to_qkv.weight");
+        const WT* ff1 = find(t + ".ff.net.0.proj.weight");
+        const WT* ff1b = find(t + ".ff.net.0.proj.bias");
+        const WT* q = find(t + ".attn2.to_q.weight");
+        const WT *g1 = find(t + ".norm1.weight"), *b1 = find(t + ".norm1.bias");
+        const WT *g2 = find(t + ".norm2.weight"), *b2 = find(t + ".norm2.bias");
+        const WT *g3 = find(t + ".norm3.weight"), *b3 = find(t + ".norm3.bias");
+        if (!qkv || !ff1 || !ff1b || !q || !g1 || !b1 || !g2 || !b2 || !g3 || !b3) return 0;  // folding stays off
+        const int C = static_cast<int>(q->shape[0]);
+        if (qkv->dtype != 1 || ff1->dtype != 1 || q->dtype != 1 || qkv->shape[1] != C || ff1->shape[1] != C) return 0;
+        LnFold& f = v[i];
+        const size_t n3 = static_cast<size_t>(qkv->shape[0]), n8 = static_cast<size_t>(ff1->shape[0]);
+        f.qkv_w = static_cast<__half*>(persistent(n3 * C * 2, false));
+        f.qkv_cs = static_cast<float*>(persistent(n3 * 4, true));
+        f.qkv_b = static_cast<float*>(persistent(n3 * 4, true));
+        f.ff1_w = static_cast<__half*>(persistent(n8 * C * 2, false));
+        f.ff1_cs = static_cast<float*>(persistent(n8 * 4, true));
+        f.ff1_b = static_cast<float*>(persistent(n8 * 4, true));
+        f.q_w = static_cast<__half*>(persistent(static_cast<size_t>(C) * C * 2, false));
+        f.q_beta = static_cast<float*>(persistent(static_cast<size_t>(C) * 4, true));
+        f.wscore = static_cast<__half*>(persistent(static_cast<size_t>(3) * HP * C * 2, true));
+        f.ws_cs = static_cast<float*>(persistent(static_cast<size_t>(3) * HP * 4, true));
+        f.ws_b = static_cast<float*>(persistent(static_cast<size_t>(3) * HP * 4, true));
+        if (!f.qkv_w || !f.qkv_cs || !f.qkv_b || !f.ff1_w || !f.ff1_cs || !f.ff1_b || !f.q_w || !f.q_beta || !f.wscore ||
+            !f.ws_cs || !f.ws_b)
+            return -1;
+        auto H = [](const WT* w) { return static_cast<const __half*>(w->dev); };
+        auto F = [](const WT* w) { return static_cast<const float*>(w->dev); };
+        if (launch_ln_fold_weights(H(qkv), static_cast<int>(n3), C, C, F(g1), F(b1), nullptr, f.qkv_w, f.qkv_cs, f.qkv_b, 0) ||
+            launch_ln_fold_weights(H(ff1), static_cast<int>(n8), C, C, F(g3), F(b3), F(ff1b), f.ff1_w, f.ff1_cs, f.ff1_b, 0) ||
+            launch_ln_fold_weights(H(q), C, C, C, F(g2), F(b2), nullptr, f.q_w, nullptr, f.q_beta, 0))
+            return fail(std::string("LayerNorm weight folding failed: ") + kernels_last_error());
+        launches_ += 3;
+    }
+    if (cudaStreamSynchronize(0) != cudaSuccess) return fail("LayerNorm weight folding: device error");
+    ln_ = std::move(v);
     return 0;
 }
 
@@ -831,6 +913,12 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
     const int seq = x.H * x.W, batch = x.N;
     const long long rows = x.rows();
     const std::string t = p + ".transformer_blocks.0";
+    const int tf = e.tf_index(p);
+    // The three LayerNorms of the block are folded into the contractions that consume them (gemm_tc.h; the reference fuses
+    // each into one plugin op in front of the GEMM, models.py:304-365): the producer of h emits per-row partial sums, the
+    // consumer multiplies the raw rows by gamma-scaled weights and normalises in its epilogue. Needs C % 32 == 0.
+    const bool fl = e.fold_ln() && (C % 32) == 0 && e.fold_cross();
+    float2* st = fl ? static_cast<float2*>(b.raw(static_cast<size_t>(rows) * (C / 32) * sizeof(float2))) : nullptr;
     Act n = b.groupnorm(x, Act{}, p + ".norm", 1e-6f, 0);
     Act h = b.like(x, C);
     int wr = 0, wc = 0;
@@ -838,21 +926,27 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         Lin l;
         l.A0 = n.p; l.lda0 = C; l.K0 = C; l.M = rows;
         l.W = b.W16(p + ".proj_in.weight", &wr, &wc); l.ldw = C; l.N = C;
-        l.bias = b.F32(p + ".proj_in.bias"); l.out = h.p;
+        l.bias = b.F32(p + ".proj_in.bias"); l.out = h.p; l.stats_out = st;
         b.linear(l);
     }
     b.release(n);
     // self-attention
-    Act tmp = b.like(x, C);
-    b.layernorm(h, t + ".norm1", tmp.p);
+    Act tmp;
+    if (!fl) {
+        tmp = b.like(x, C);
+        b.layernorm(h, t + ".norm1", tmp.p);
+    }
     Act qkv = b.like(x, 3 * C);
     {
         Lin l;
-        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = b.W16(t + ".attn1.to_qkv.weight"); l.ldw = C; l.N = 3 * C; l.out = qkv.p;
+        l.A0 = fl ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = fl ? e.ln(tf).qkv_w : b.W16(t + ".attn1.to_qkv.weight"); l.ldw = C; l.N = 3 * C; l.out = qkv.p;
+        if (fl) {
+            l.ln_stats = st; l.ln_colsum = e.ln(tf).qkv_cs; l.ln_C = C; l.bias = e.ln(tf).qkv_b;
+        }
         b.linear(l);
     }
-    b.release(tmp);
+    if (!fl) b.release(tmp);
     Act att = b.like(x, C);
     if (b.ok)
         b.attention(qkv.p, 3 * C, qkv.p + C, 3 * C, qkv.p + 2 * C, 3 * C, att.p, C, seq, seq, heads, d, batch,
@@ -863,7 +957,7 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         Lin l;
         l.A0 = att.p; l.lda0 = C; l.K0 = C; l.M = rows;
         l.W = b.W16(t + ".attn1.to_out.0.weight"); l.ldw = C; l.N = C;
-        l.bias = b.F32(t + ".attn1.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+        l.bias = b.F32(t + ".attn1.to_out.0.bias"); l.res = h.p; l.ldr = C; l.out = h.p; l.stats_out = st;
         b.linear(l);
     }
     b.release(att);
@@ -871,24 +965,28 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
     // (scores = LN2(h) (scale K_h Wq_h)^T) and the output projection into the values (out = P (V_h Wo_h^T)), both
     // prepared by the condition plan: two skinny contractions, softmax over the 14 tokens in the first one's epilogue.
     // Sample groups [uncond | cond | texture-guidance] pick their context through the batch coordinate.
-    tmp = b.like(x, C);
-    b.layernorm(h, t + ".norm2", tmp.p);
+    if (!fl) {
+        tmp = b.like(x, C);
+        b.layernorm(h, t + ".norm2", tmp.p);
+    }
     const int T = cfg.enc_tokens;
     if (e.fold_cross()) {
         const int HP = heads * 16;
-        const int tf = e.tf_index(p);
         const long long grp_rows = rows / 3;
         Act P = b.like(x, HP);
         if (b.ok) {
             Builder::Bmm g;
-            g.A = tmp.p; g.lda = C; g.a_zs1 = grp_rows * C;
-            g.B = e.wscore(tf); g.ldb = C; g.b_zs1 = static_cast<long long>(HP) * C;
+            g.A = fl ? h.p : tmp.p; g.lda = C; g.a_zs1 = grp_rows * C;
+            g.B = fl ? e.ln(tf).wscore : e.wscore(tf); g.ldb = C; g.b_zs1 = static_cast<long long>(HP) * C;
             g.M = static_cast<int>(grp_rows); g.N = HP; g.K = C; g.nz1 = 3;
             g.out = P.p; g.ldc = HP; g.out_zs1 = grp_rows * HP;
             g.flags = EPI_SOFTMAX16; g.aux = T; g.label = "cross_scores";
+            if (fl) {
+                g.ln_stats = st; g.ln_colsum = e.ln(tf).ws_cs; g.ln_C = C; g.bias = e.ln(tf).ws_b; g.bias_zs1 = HP;
+            }
             b.bmm(g);
         }
-        b.release(tmp);
+        if (!fl) b.release(tmp);
         if (b.ok) {
             Builder::Bmm g;
             g.A = P.p; g.lda = HP; g.a_zs1 = grp_rows * HP;
@@ -896,7 +994,7 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
             g.M = static_cast<int>(grp_rows); g.N = C; g.K = HP; g.nz1 = 3;
             g.out = h.p; g.ldc = C; g.out_zs1 = grp_rows * C;
             g.bias = b.F32(t + ".attn2.to_out.0.bias");
-            g.res = h.p; g.ldr = C; g.res_zs1 = grp_rows * C; g.label = "cross_out";
+            g.res = h.p; g.ldr = C; g.res_zs1 = grp_rows * C; g.label = "cross_out"; g.stats_out = st;
             b.bmm(g);
         }
         b.release(P);
@@ -925,17 +1023,22 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.release(att);
     }
     // GEGLU feed-forward
-    tmp = b.like(x, C);
-    b.layernorm(h, t + ".norm3", tmp.p);
+    if (!fl) {
+        tmp = b.like(x, C);
+        b.layernorm(h, t + ".norm3", tmp.p);
+    }
     Act g = b.like(x, 4 * C);
     {
         Lin l;
-        l.A0 = tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
-        l.bias = b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
+        l.A0 = fl ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = fl ? e.ln(tf).ff1_w : b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
+        l.bias = fl ? e.ln(tf).ff1_b : b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
+        if (fl) {
+            l.ln_stats = st; l.ln_colsum = e.ln(tf).ff1_cs; l.ln_C = C;
+        }
         b.linear(l);
     }
-    b.release(tmp);
+    if (!fl) b.release(tmp);
     {
         Lin l;
         l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
@@ -953,7 +1056,7 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.linear(l);
     }
     b.release(h);
-    (void)e;
+    if (st) b.release_raw(st);
     return out;
 }
 
@@ -1486,6 +1589,15 @@ int Engine::build_cond_plan() {
                 g.alpha = scale; g.label = "fold_scores";
                 b.bmm(g);
             }
+            if (!ln_.empty()) {  // same operand through Wq diag(norm2.weight): the LayerNorm-folded score contraction
+                Builder::Bmm g;
+                g.A = Kc; g.lda = 2 * C; g.a_zs1 = d;
+                g.B = ln_[i].q_w; g.ldb = C; g.b_zs1 = static_cast<long long>(d) * C; g.b_mn = 1;
+                g.M = T; g.N = C; g.K = d; g.nz1 = heads;
+                g.out = ln_[i].wscore + static_cast<size_t>(slot) * HP * C; g.ldc = C; g.out_zs1 = 16LL * C;
+                g.alpha = scale; g.label = "fold_scores_ln";
+                b.bmm(g);
+            }
             {   // Wout[slot][:, h*16 + j] = Wo[:, h*d:(h+1)*d] V_c,h[j,:]^T
                 Builder::Bmm g;
                 g.A = Wo; g.lda = C; g.a_zs1 = d;
@@ -1496,6 +1608,21 @@ int Engine::build_cond_plan() {
                 b.bmm(g);
             }
         }
+    }
+    for (size_t i = 0; i < tf_names_.size() && b.ok && !ln_.empty(); ++i) {
+        int C = 0;
+        b.W16(tf_names_[i] + ".transformer_blocks.0.attn2.to_q.weight", &C, nullptr);
+        if (!b.ok) break;
+        const LnFold f = ln_[i];
+        const __half* kvp = cross_kv_[i];
+        const float scale = 1.0f / sqrtf(static_cast<float>(C / heads));
+        cond_plan_.add(K_OTHER, [=](cudaStream_t st) -> int {
+            if (launch_cross_ln_finish(f.wscore, kvp, f.q_beta, C, heads, T, scale, f.ws_cs, f.ws_b, st)) {
+                eng->err_ = kernels_last_error();
+                return -1;
+            }
+            return 1;
+        });
     }
     if (!b.ok) {
         cond_plan_.clear();
@@ -1939,6 +2066,13 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "fold_cross") {
         opt_fold_cross_ = value;
+        unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fold_ln") {
+        opt_fold_ln_ = value;
         unet_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();

@@ -137,6 +137,8 @@ class Engine {
     int check_device_error();
     int grow_arena(size_t bytes);
     bool fold_cross() const { return opt_fold_cross_ != 0; }
+    bool fold_ln() const { return opt_fold_ln_ != 0 && !ln_.empty(); }
+    const LnFold& ln(int i) const { return ln_[i]; }
     int tf_index(const std::string& prefix) const {
         for (size_t i = 0; i < tf_names_.size(); ++i)
             if (tf_names_[i] == prefix) return static_cast<int>(i);
@@ -201,6 +203,21 @@ class Engine {
     std::vector<__half*> wscore_;    // per layer: (3, heads*16, C)  scale * K_h Wq_h, zero rows for the pad tokens
     std::vector<__half*> wout_;      // per layer: (3, C, heads*16)  Wo_h V_h^T
     int opt_fold_cross_ = 1;
+    // LayerNorm folded into the consuming contraction (gemm_tc.h): per transformer layer, prepared at finalize_weights
+    // (gamma-scaled weights, their row sums, W beta) and per brush (the folded cross-attention score operand)
+    struct LnFold {
+        __half* qkv_w = nullptr;   // (3C, C)  to_qkv diag(norm1.weight)
+        float *qkv_cs = nullptr, *qkv_b = nullptr;
+        __half* ff1_w = nullptr;   // (8C, C)  ff.net.0.proj diag(norm3.weight), GEGLU row order
+        float *ff1_cs = nullptr, *ff1_b = nullptr;
+        __half* q_w = nullptr;     // (C, C)   attn2.to_q diag(norm2.weight)
+        float* q_beta = nullptr;   // (C)      attn2.to_q norm2.bias
+        __half* wscore = nullptr;  // (3, heads*16, C) per brush: scale * K_h (Wq diag(gamma))_h
+        float *ws_cs = nullptr, *ws_b = nullptr;  // (3, heads*16)
+    };
+    std::vector<LnFold> ln_;
+    int opt_fold_ln_ = 1;
+    int prepare_ln_fold();
     std::vector<std::string> tf_names_;  // transformer prefixes in execution order
     bool cond_set_ = false;
 

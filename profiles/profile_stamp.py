@@ -23,6 +23,8 @@ ap.add_argument("--tag", default="r1")
 ap.add_argument("--stamps", type=int, default=1)
 ap.add_argument("--no-op-profile", action="store_true")
 ap.add_argument("--no-graph", action="store_true")
+ap.add_argument("--profiler-range", action="store_true",
+                help="cudaProfilerStart/Stop around the measured stamps (ncu --profile-from-start off)")
 ap.add_argument("--ablate", action="store_true",
                 help="graph-mode stamp time with each kernel family skipped in turn (in-situ cost = difference)")
 a = ap.parse_args()
@@ -68,11 +70,16 @@ torch.cuda.synchronize()
 if not a.no_op_profile:
     eng.set_option("profile", 1)
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+if a.profiler_range:
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
 t0.record()
 for _ in range(a.stamps):
     eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
 t1.record()
 torch.cuda.synchronize()
+if a.profiler_range:
+    torch.cuda.profiler.stop()
 print("ms per stamp (with per-op events)" if not a.no_op_profile else "ms per stamp", t0.elapsed_time(t1) / a.stamps)
 if not a.no_op_profile:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -140,3 +140,36 @@ def test_handler_twin_is_the_unmodified_handler(reference_server):
     h2 = handler.InpaintWebSocketHandler(model=None, model_info_str="trt", debug_dir=None)
     h2.on_message(frames[1])
     assert h2.written == []
+
+
+def test_fast_handler_uses_the_u8_path_and_answers_errors(reference_server):
+    """opt-in subclass of the reference handler: uint8 wire image -> stamp_u8, error frame on failure."""
+    handler, _, server_io = reference_server
+    from diffusiontexturepainting_b200 import fast_handler as fh
+    Fast = fh.make_fast_handler(handler.InpaintWebSocketHandler, server_io)
+    R = 32
+
+    class U8Model(Recorder):
+        def stamp_u8(self, canvas_u8_hwc, **settings):
+            assert canvas_u8_hwc.dtype == np.uint8 and canvas_u8_hwc.shape == (R, R, 4)
+            self.calls.append(("stamp_u8", {k: type(v).__name__ for k, v in sorted(settings.items())}))
+            return torch.from_numpy(canvas_u8_hwc[None, :, :, :3].copy()) // 2
+
+    m = U8Model(R)
+    h = Fast(model=m, model_info_str="trt", debug_dir=None)
+    brush_frame, stamp_frame = twin.synthetic_frames(R, steps=5)
+    h.on_message(brush_frame)
+    h.on_message(stamp_frame)
+    assert [c[0] for c in m.calls] == ["set_brush", "generate", "stamp_u8"]
+    resp = server_io.decode_response(h.written[1][0])
+    assert resp["type"] == server_io.RequestType.RETURN_STAMP.value
+    assert np.array_equal(resp["image"], twin.binary_to_image(stamp_frame, 14)[..., :3] // 2)
+    # a failure is answered, not swallowed
+    h2 = Fast(model=None, model_info_str="trt", debug_dir=None)
+    h2.on_message(stamp_frame)
+    assert len(h2.written) == 1 and h2.written[0][1] is True
+    msg = fh.decode_error_frame(h2.written[0][0])
+    assert msg is not None and "AttributeError" in msg
+    assert fh.decode_error_frame(h.written[1][0]) is None
+    h2.on_message(b"\x07" + stamp_frame[1:])  # unknown request type
+    assert "Unknown binary request type" in fh.decode_error_frame(h2.written[1][0])

@@ -285,7 +285,13 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     eng.set_option("flash", 0)
     outs["noflash"] = model.generate(canvas, init_latents=lat, **settings).clone()
     eng.set_option("flash", 1)
-    for k in ("unfolded", "noflash"):
+    eng.set_option("fold_ln", 0)   # standalone LayerNorm kernels instead of the LayerNorm folded into QKV / scores / FF1
+    outs["ln_kernels"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    n_unfolded = eng.counter("unet_plan_ops")
+    eng.set_option("fold_ln", 1)
+    outs["ln_folded"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    assert eng.counter("unet_plan_ops") < n_unfolded  # three launches fewer per transformer block
+    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
