@@ -167,33 +167,55 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x0, int C0, const __h
     __syncthreads();
     if (s_ticket != chunks - 1) return;
     __threadfence();
-    float* stat = reinterpret_cast<float*>(sm_acc);  // [groups][2] mean, rstd
+    // The whole CTA folds the partials (round 1 used one thread per group: 512 chunks at 8 loads in flight were 64 serial L2
+    // round trips, ~60 us of the 95 us this kernel took on the 512 x 512 VAE tensors): nl threads per group take the
+    // chunks l, l + nl, ... in order, then thread g adds the nl sub-sums in order - still a fixed summation order.
+    double* dsum = reinterpret_cast<double*>(sm_acc);  // [groups][nl][2]; sm_acc is dead (read above, barrier passed)
+    const int nl = max(1, min(static_cast<int>(blockDim.x) / groups, 32));
+    {
+        const int g = threadIdx.x / nl, l = threadIdx.x - g * nl;
+        if (g < groups) {
+            double a = 0.0, b = 0.0;
+            const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * groups + g;
+            int ch = l;
+            for (; ch + 3 * nl < chunks; ch += 4 * nl) {
+                float2 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = __ldcg(pp + static_cast<long long>(ch + u * nl) * groups);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a += static_cast<double>(t[u].x);
+                    b += static_cast<double>(t[u].y);
+                }
+            }
+            for (; ch < chunks; ch += nl) {
+                const float2 t = __ldcg(pp + static_cast<long long>(ch) * groups);
+                a += static_cast<double>(t.x);
+                b += static_cast<double>(t.y);
+            }
+            dsum[(g * nl + l) * 2] = a;
+            dsum[(g * nl + l) * 2 + 1] = b;
+        }
+    }
+    __syncthreads();
+    double mean_d = 0.0, rstd_d = 0.0;
     if (threadIdx.x < groups) {
         double a = 0.0, b = 0.0;
-        // L2 loads (the partials were written by other CTAs; __threadfence + ticket order them), 8 in flight per thread
-        const float2* pp = reinterpret_cast<const float2*>(partial) + static_cast<long long>(n) * chunks * groups + threadIdx.x;
-        int ch = 0;
-        for (; ch + 8 <= chunks; ch += 8) {
-            float2 t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldcg(pp + static_cast<long long>(ch + u) * groups);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                a += static_cast<double>(t[u].x);
-                b += static_cast<double>(t[u].y);
-            }
-        }
-        for (; ch < chunks; ++ch) {
-            const float2 t = __ldcg(pp + static_cast<long long>(ch) * groups);
-            a += static_cast<double>(t.x);
-            b += static_cast<double>(t.y);
+        for (int l = 0; l < nl; ++l) {
+            a += dsum[(threadIdx.x * nl + l) * 2];
+            b += dsum[(threadIdx.x * nl + l) * 2 + 1];
         }
         const double count = static_cast<double>(HW) * cpg;
-        const double mean = a / count;
-        double var = b / count - mean * mean;
+        mean_d = a / count;
+        double var = b / count - mean_d * mean_d;
         if (var < 0.0) var = 0.0;
-        stat[2 * threadIdx.x] = static_cast<float>(mean);
-        stat[2 * threadIdx.x + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        rstd_d = 1.0 / sqrt(var + static_cast<double>(eps));
+    }
+    __syncthreads();  // dsum fully consumed before stat (same storage) is written
+    float* stat = reinterpret_cast<float*>(sm_acc);  // [groups][2] mean, rstd
+    if (threadIdx.x < groups) {
+        stat[2 * threadIdx.x] = static_cast<float>(mean_d);
+        stat[2 * threadIdx.x + 1] = static_cast<float>(rstd_d);
     }
     __syncthreads();
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {

@@ -103,6 +103,19 @@ struct Plan {
     }
 };
 
+// LayerNorm folded into the consuming contraction (gemm_tc.h): per transformer layer, prepared at finalize_weights
+// (gamma-scaled weights, their row sums, W beta) and per brush (the folded cross-attention score operand)
+struct LnFold {
+    __half* qkv_w = nullptr;   // (3C, C)  to_qkv diag(norm1.weight)
+    float *qkv_cs = nullptr, *qkv_b = nullptr;
+    __half* ff1_w = nullptr;   // (8C, C)  ff.net.0.proj diag(norm3.weight), GEGLU row order
+    float *ff1_cs = nullptr, *ff1_b = nullptr;
+    __half* q_w = nullptr;     // (C, C)   attn2.to_q diag(norm2.weight)
+    float* q_beta = nullptr;   // (C)      attn2.to_q norm2.bias
+    __half* wscore = nullptr;  // (3, heads*16, C) per brush: scale * K_h (Wq diag(gamma))_h
+    float *ws_cs = nullptr, *ws_b = nullptr;  // (3, heads*16)
+};
+
 class Engine {
    public:
     explicit Engine(const dtp_config& cfg);
@@ -203,18 +216,6 @@ class Engine {
     std::vector<__half*> wscore_;    // per layer: (3, heads*16, C)  scale * K_h Wq_h, zero rows for the pad tokens
     std::vector<__half*> wout_;      // per layer: (3, C, heads*16)  Wo_h V_h^T
     int opt_fold_cross_ = 1;
-    // LayerNorm folded into the consuming contraction (gemm_tc.h): per transformer layer, prepared at finalize_weights
-    // (gamma-scaled weights, their row sums, W beta) and per brush (the folded cross-attention score operand)
-    struct LnFold {
-        __half* qkv_w = nullptr;   // (3C, C)  to_qkv diag(norm1.weight)
-        float *qkv_cs = nullptr, *qkv_b = nullptr;
-        __half* ff1_w = nullptr;   // (8C, C)  ff.net.0.proj diag(norm3.weight), GEGLU row order
-        float *ff1_cs = nullptr, *ff1_b = nullptr;
-        __half* q_w = nullptr;     // (C, C)   attn2.to_q diag(norm2.weight)
-        float* q_beta = nullptr;   // (C)      attn2.to_q norm2.bias
-        __half* wscore = nullptr;  // (3, heads*16, C) per brush: scale * K_h (Wq diag(gamma))_h
-        float *ws_cs = nullptr, *ws_b = nullptr;  // (3, heads*16)
-    };
     std::vector<LnFold> ln_;
     int opt_fold_ln_ = 1;
     int prepare_ln_fold();
