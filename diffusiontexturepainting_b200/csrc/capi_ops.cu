@@ -95,6 +95,22 @@ int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int
     return finish(op, r, bias, residual, ldr, out, ldc, flags, alpha, hw_out, (cudaStream_t)stream);
 }
 
+int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, const void* S1, int CS1, int Nimg, int H, int W,
+                            const void* Wt, int Cout, const float* bias, void* out, int BN, int splits, void* stream) {
+    GemmOp op;
+    if (BN <= 0) {
+        GemmOp probe;
+        int r0 = gemm_setup_conv3x3(&probe, (const __half*)A0, C0, nullptr, 0, Nimg, H, W, (const __half*)Wt, Cout, 128, 1, 0,
+                                    (const __half*)S0, CS0, (const __half*)S1, CS1);
+        if (r0) return finish(probe, r0, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+        gemm_pick_config(probe.grid_m, Cout, probe.p.num_kb,
+                         (probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0, &BN, &splits);
+    }
+    int r = gemm_setup_conv3x3(&op, (const __half*)A0, C0, nullptr, 0, Nimg, H, W, (const __half*)Wt, Cout, BN, splits, 0,
+                               (const __half*)S0, CS0, (const __half*)S1, CS1);
+    return finish(op, r, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+}
+
 int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
                long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
                long long out_zs2, float alpha, int flags, int BN, void* stream) {

@@ -43,6 +43,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// three-input maximum (FMNMX3 on sm_100): halves the instruction count of the row-maximum pass
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // DCH: 64-wide chunks of the (padded) head dim; KV_STAGES: ring depth of the K and V tiles
@@ -503,13 +509,13 @@ __global__ void __launch_bounds__(384, 1)
             if (kv_valid == 128) {
                 float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; i += 4) {
-                    b0 = fmaxf(b0, __uint_as_float(raw[i]));
-                    b1 = fmaxf(b1, __uint_as_float(raw[i + 1]));
-                    b2 = fmaxf(b2, __uint_as_float(raw[i + 2]));
-                    b3 = fmaxf(b3, __uint_as_float(raw[i + 3]));
+                for (int i = 0; i < 128; i += 8) {
+                    b0 = max3(b0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                    b1 = max3(b1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+                    b2 = max3(b2, __uint_as_float(raw[i + 4]), __uint_as_float(raw[i + 5]));
+                    b3 = max3(b3, __uint_as_float(raw[i + 6]), __uint_as_float(raw[i + 7]));
                 }
-                bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+                bm = max3(max3(b0, b1, b2), b3, -INFINITY);
             } else {
 #pragma unroll
                 for (int i = 0; i < 128; ++i) {
@@ -784,13 +790,13 @@ __global__ void __launch_bounds__(256, 1)
             if (kv_valid == 128) {
                 float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; i += 4) {
-                    b0 = fmaxf(b0, __uint_as_float(raw[i]));
-                    b1 = fmaxf(b1, __uint_as_float(raw[i + 1]));
-                    b2 = fmaxf(b2, __uint_as_float(raw[i + 2]));
-                    b3 = fmaxf(b3, __uint_as_float(raw[i + 3]));
+                for (int i = 0; i < 128; i += 8) {
+                    b0 = max3(b0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+                    b1 = max3(b1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+                    b2 = max3(b2, __uint_as_float(raw[i + 4]), __uint_as_float(raw[i + 5]));
+                    b3 = max3(b3, __uint_as_float(raw[i + 6]), __uint_as_float(raw[i + 7]));
                 }
-                bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+                bm = max3(max3(b0, b1, b2), b3, -INFINITY);
             } else {
 #pragma unroll
                 for (int i = 0; i < 128; ++i) {

@@ -76,45 +76,46 @@ __device__ __forceinline__ void store_f32_chunk(float* out, const float (&v)[32]
 // folded LayerNorm: (rstd, -rstd * mean) of A row `grow` from the producer's per-chunk partial sums (gemm_tc.h)
 __device__ __forceinline__ void ln_row_coef(const GemmParams& p, long long grow, float& ln_r, float& ln_nm) {
     const float2* sp = p.ln_stats + grow;
-    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
-    int ch = 0;
-    for (; ch + 4 <= p.ln_chunks; ch += 4) {  // four independent loads in flight
-        const float2 a = __ldcg(sp + static_cast<long long>(ch) * p.ln_rows);
-        const float2 b = __ldcg(sp + static_cast<long long>(ch + 1) * p.ln_rows);
-        const float2 c = __ldcg(sp + static_cast<long long>(ch + 2) * p.ln_rows);
-        const float2 d = __ldcg(sp + static_cast<long long>(ch + 3) * p.ln_rows);
-        s0 += a.x + b.x;
-        s1 += c.x + d.x;
-        q0 += a.y + b.y;
-        q1 += c.y + d.y;
+    float s = 0.0f, q = 0.0f;
+    // the warp issues in order: every load of a batch must be issued before the first add that consumes one, or each
+    // partial costs a full L2 round trip (C / 32 = 10 / 20 / 40 partials per row at the UNet widths)
+    for (int ch = 0; ch < p.ln_chunks; ch += 10) {
+        float2 t[10];
+#pragma unroll
+        for (int u = 0; u < 10; ++u)
+            t[u] = (ch + u < p.ln_chunks) ? __ldcg(sp + static_cast<long long>(ch + u) * p.ln_rows) : make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int u = 0; u < 10; ++u) {
+            s += t[u].x;
+            q += t[u].y;
+        }
     }
-    for (; ch < p.ln_chunks; ++ch) {
-        const float2 a = __ldcg(sp + static_cast<long long>(ch) * p.ln_rows);
-        s0 += a.x;
-        q0 += a.y;
-    }
-    const float mean = (s0 + s1) * p.ln_inv_c;
-    const float var = fmaxf((q0 + q1) * p.ln_inv_c - mean * mean, 0.0f);
+    const float mean = s * p.ln_inv_c;
+    const float var = fmaxf(q * p.ln_inv_c - mean * mean, 0.0f);
     ln_r = rsqrtf(var + p.ln_eps);
     ln_nm = -ln_r * mean;
 }
-// (sum, sum of squares) of the 32 values as they are stored (fp16-rounded), for a following folded LayerNorm
+// (sum, sum of squares) of 32 output values for a following folded LayerNorm. Taken before the fp16 rounding of the store:
+// the rounding errors are zero-mean and 2^-11 relative, far below what the statistics resolve, and the conversion round
+// trip would double the instruction count of this (exposed) part of the epilogue.
 __device__ __forceinline__ void emit_row_stats(const GemmParams& p, long long grow, int col0, const float (&v)[32]) {
-    float s = 0.0f, q = 0.0f;
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float x = __half2float(__float2half_rn(v[i]));
-        s += x;
-        q = fmaf(x, x, q);
+    for (int i = 0; i < 32; i += 2) {
+        s0 += v[i];
+        s1 += v[i + 1];
+        q0 = fmaf(v[i], v[i], q0);
+        q1 = fmaf(v[i + 1], v[i + 1], q1);
     }
-    p.stats_out[static_cast<long long>(col0 >> 5) * p.stats_rows + grow] = make_float2(s, q);
+    p.stats_out[static_cast<long long>(col0 >> 5) * p.stats_rows + grow] = make_float2(s0 + s1, q0 + q1);
 }
 
 // bias_chunk: 32 floats for columns col0.. (shared memory in the main kernel, global in the finalize kernel), or nullptr.
 // grow: row index in the statistics buffers ((z2 * nz1 + z1) * M + row); colsum_chunk: like bias_chunk, for the folded LayerNorm
 __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long out_off, long long res_off, int row,
                                                  int col0, float (&v)[32], const float* bias_chunk,
-                                                 long long grow = 0, const float* colsum_chunk = nullptr) {
+                                                 long long grow = 0, const float* colsum_chunk = nullptr,
+                                                 bool feat = true) {
     const int N = p.N;
     const int ncols = min(32, N - col0);
     if (ncols <= 0) return;
@@ -139,7 +140,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
             for (int i = 0; i < 4; ++i) rraw[i] = __ldg(reinterpret_cast<const uint4*>(rp) + i);
         }
     }
-    if (p.ln_stats != nullptr) {
+    if (feat && p.ln_stats != nullptr) {
         float ln_r, ln_nm;
         ln_row_coef(p, grow, ln_r, ln_nm);
 #pragma unroll
@@ -253,7 +254,7 @@ __device__ __forceinline__ void epilogue_store32(const GemmParams& p, long long 
     }
     __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc + col0;
     store_half_chunk(out, v, ncols, (p.ldc & 7) == 0 && (out_off & 7) == 0);
-    if (p.stats_out != nullptr) emit_row_stats(p, grow, col0, v);
+    if (feat && p.stats_out != nullptr) emit_row_stats(p, grow, col0, v);
 }
 
 // bounded mbarrier wait: a descriptor / byte-count bug must trap, not hang the GPU
@@ -352,10 +353,14 @@ __device__ __forceinline__ int tile_row(const GemmParams& p, const TileCoord& c,
 // OCC = 2: light configuration (few stages, BN <= 128 -> <= 256 TMEM columns, <= 102 registers) so that two CTAs share an SM:
 // the next kernel's CTAs become resident while this one drains (PDL overlap instead of a kernel-boundary bubble) and two
 // tiles interleave their load latency / mainloop / epilogue on one SM.
-template <int BN, int STAGES, int CL, int OCC = 1>
+// FEAT = 1: the instantiation that can fold a LayerNorm into its epilogue and emit row statistics (gemm_tc.h). Kept apart
+// from the plain one because the epilogue sits at the register cap: the extra live values cost spills in EVERY op when
+// compiled into one kernel (measured: +16 us on an unrelated split-K convolution).
+template <int BN, int STAGES, int CL, int OCC = 1, int FEAT = 0>
 __global__ void __launch_bounds__(320, OCC)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBL,
+                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                    const __grid_constant__ GemmParams p) {
     // CL == 2: CTA pair (cta_group::2). One MMA spans both SMs (M = 256); each CTA's shared memory holds its own 128 rows
     // of A and HALF of the B tile (rows [rank*BN/2, +BN/2)), which halves the shared-memory traffic per CTA - the limit of
@@ -399,6 +404,10 @@ __global__ void __launch_bounds__(320, OCC)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
+        if (p.sc_blocks > 0) {
+            tma_prefetch_desc(&mapA2);
+            tma_prefetch_desc(&mapA3);
+        }
         tma_prefetch_desc(&mapB);
         if (p.n_last > 0) tma_prefetch_desc(&mapBL);
         for (int s = 0; s < STAGES; ++s) {
@@ -483,7 +492,14 @@ __global__ void __launch_bounds__(320, OCC)
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        if (cb < p.cblocks0)
+                        if (tap >= 9) {
+                            // fused 1x1 shortcut: unshifted boxes of the shortcut's own sources
+                            const int sb = kb - 9 * p.cblocks;
+                            if (sb < p.sc_blocks0)
+                                tma4<CL>(sa, &mapA2, &full_bar[stage], sb * 64, c.x0, c.y0, c.img0);
+                            else
+                                tma4<CL>(sa, &mapA3, &full_bar[stage], (sb - p.sc_blocks0) * 64, c.x0, c.y0, c.img0);
+                        } else if (cb < p.cblocks0)
                             tma4<CL>(sa, &mapA0, &full_bar[stage], cb * 64, c.x0 + kx - 1, c.y0 + ky - 1, c.img0);
                         else
                             tma4<CL>(sa, &mapA1, &full_bar[stage], (cb - p.cblocks0) * 64, c.x0 + kx - 1, c.y0 + ky - 1,
@@ -594,7 +610,7 @@ __global__ void __launch_bounds__(320, OCC)
         int acc = 0;
         uint32_t acc_phase = 0;
         const bool col_bias = p.bias != nullptr && (p.flags & EPI_BIAS_M) == 0;
-        const bool ln_on = p.ln_stats != nullptr;
+        const bool ln_on = FEAT != 0 && p.ln_stats != nullptr;
         const bool fused_reduce = p.splits > 1 && p.tile_counters != nullptr;
         // 32-byte aligned full-width fp16 rows (st.global.v8 / 16-byte residual loads) and an epilogue the fast path covers
         const bool fast_epi =
@@ -705,7 +721,7 @@ __global__ void __launch_bounds__(320, OCC)
                                             rres[it % RD][i] = __ldg(reinterpret_cast<const uint4*>(rrow + 64 * (it + RD)) + i);
                                     }
                                 }
-                                if (p.stats_out != nullptr) emit_row_stats(p, grow, c.n0 + cc, v);
+                                if (FEAT != 0 && p.stats_out != nullptr) emit_row_stats(p, grow, c.n0 + cc, v);
                                 __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc +
                                               c.n0 + cc;
 #pragma unroll
@@ -792,7 +808,7 @@ __global__ void __launch_bounds__(320, OCC)
                         store_f32_chunk(ws, v, ncols, (p.N & 3) == 0);
                     } else {
                         epilogue_store32(p, out_off, res_off, row, c.n0 + cc, v, col_bias ? sbias + cc : nullptr, grow,
-                                         scolsum + cc);
+                                         scolsum + cc, FEAT != 0);
                     }
                 }
             }
@@ -874,7 +890,7 @@ __global__ void __launch_bounds__(320, OCC)
                         v[4 * j + 3] = t4.w;
                     }
                     epilogue_store32(p, out_off, res_off, orow, col0, v, col_bias ? sbias + ch * 32 : nullptr,
-                                     static_cast<long long>(c.z2 * p.nz1 + c.z1) * p.M + orow, scolsum + ch * 32);
+                                     static_cast<long long>(c.z2 * p.nz1 + c.z1) * p.M + orow, scolsum + ch * 32, FEAT != 0);
                 }
             }
             if (++acc == NACC) {
@@ -1095,6 +1111,8 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
     } else {
         op->mapA1 = op->mapA0;
     }
+    op->mapA2 = op->mapA0;
+    op->mapA3 = op->mapA0;
     op->cluster = 1;
     if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
         if (map_rows(&op->mapBh, Wt, K0 + (A1 ? K1 : 0), N, ldw, BN > 256 ? BN / 4 : BN / 2)) return -13;
@@ -1127,7 +1145,8 @@ static int largest_divisor_le(int n, int cap) {
 }
 
 int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, int C1, int Nimg, int H, int W,
-                       const __half* Wt, int Cout, int BN, int splits, int w_blocked) {
+                       const __half* Wt, int Cout, int BN, int splits, int w_blocked, const __half* S0, int CS0,
+                       const __half* S1, int CS1) {
     params_defaults(op->p);
     GemmParams& p = op->p;
     const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
@@ -1138,6 +1157,13 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
         return -11;
     }
     const int C = C0 + (A1 ? C1 : 0);
+    if (S0 == nullptr) CS0 = 0;
+    if (S1 == nullptr) CS1 = 0;
+    if ((CS0 % 64) != 0 || (CS1 % 64) != 0 || (S1 != nullptr && S0 == nullptr) || ((S0 != nullptr) && w_blocked)) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "conv3x3 + shortcut needs shortcut channel counts %% 64 == 0 (CS0=%d CS1=%d)", CS0, CS1);
+        return -11;
+    }
+    const int KT = 9 * C + CS0 + CS1;  // weight row length
     p.M = Nimg * H * W;
     p.N = Cout;
     p.mode = 1;
@@ -1154,7 +1180,9 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     p.rows_valid = p.bw * p.bh * p.bn;
     p.cblocks0 = C0 / 64;
     p.cblocks = C / 64;
-    p.num_kb = 9 * p.cblocks;
+    p.sc_blocks0 = CS0 / 64;
+    p.sc_blocks = (CS0 + CS1) / 64;
+    p.num_kb = 9 * p.cblocks + p.sc_blocks;
     p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
     bind_ctx(op);
     p.ldc = Cout;
@@ -1180,9 +1208,21 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     } else {
         op->mapA1 = op->mapA0;
     }
+    op->mapA2 = op->mapA0;
+    op->mapA3 = op->mapA0;
+    const __half* srcs[2] = {S0, S1};
+    const int cs[2] = {CS0, CS1};
+    for (int i = 0; i < 2; ++i) {
+        if (srcs[i] == nullptr) continue;
+        uint64_t dims[4] = {(uint64_t)cs[i], (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t st[3] = {(uint64_t)cs[i] * 2, (uint64_t)cs[i] * 2 * W, (uint64_t)cs[i] * 2 * W * H};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+        int r = make_map_4d(i == 0 ? &op->mapA2 : &op->mapA3, srcs[i], dims, st, box);
+        if (r) return r;
+    }
     op->cluster = 1;
     if (!w_blocked && want_pair && op->grid_m >= 2 && BN >= 32) {
-        if (map_rows(&op->mapBh, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN > 256 ? BN / 4 : BN / 2)) return -13;
+        if (map_rows(&op->mapBh, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN > 256 ? BN / 4 : BN / 2)) return -13;
         op->cluster = 2;
     }
     if (w_blocked) {
@@ -1199,9 +1239,9 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
     if (BN > 256)
         op->mapB = op->mapBh;
     else
-        rm = map_rows(&op->mapB, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
+        rm = map_rows(&op->mapB, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
     if (rm) return rm;
-    return setup_ragged(op, Wt, (uint64_t)9 * C, Cout, (uint64_t)9 * C, BN);
+    return setup_ragged(op, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
 }
 
 int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, long long a_zs2, const __half* B, int ldb,
@@ -1237,6 +1277,8 @@ int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, lo
         int r = make_map_4d(&op->mapA0, A, dims, st, box);
         if (r) return r;
         op->mapA1 = op->mapA0;
+        op->mapA2 = op->mapA0;
+        op->mapA3 = op->mapA0;
     }
     if (!b_mn) {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)nz1, (uint64_t)nz2};
@@ -1416,7 +1458,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     const int cap = 2 * num_sms();
     p.tile_counters = (tiles <= cap && splitk_fused(op)) ? op->tile_counters : nullptr;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-    cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, p);
+    cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, op->mapA2, op->mapA3, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch (light): %s", cudaGetErrorString(e));
@@ -1425,7 +1467,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     return 0;
 }
 
-template <int BN, int STAGES, int STAGES2>
+template <int BN, int STAGES, int STAGES2, int FEAT>
 static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (128 * 128 + BN * 128) + (3 * STAGES + 4) * 8 + 16 + BN * 8 + 1024;
     constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 8 + 1024;
@@ -1434,9 +1476,9 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     bool& attr_set = attr_flag.here();
     if (!attr_set) {
         cudaError_t e =
-            cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+            cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, 1, 1, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+            e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2, 1, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
         if (e != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return -20;
@@ -1478,10 +1520,10 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
         attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, p);
+        e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2, 1, FEAT>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, op->mapA2, op->mapA3, p);
     } else {
         const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-        e = launch_k(gemm_tc_kernel<BN, STAGES, 1>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, p);
+        e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 1, FEAT>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, op->mapA2, op->mapA3, p);
     }
     if (e != cudaSuccess) e = cudaGetLastError();
     else e = cudaGetLastError();
@@ -1522,14 +1564,14 @@ static int max_pair_clusters() {
 }
 
 // BN = 320: CTA pairs only (a single-CTA 128 x 320 tile would need 56 KB per stage)
-template <int BN, int STAGES2>
+template <int BN, int STAGES2, int FEAT>
 static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
     constexpr int SMEM2 = STAGES2 * (128 * 128 + BN * 64) + (3 * STAGES2 + 4) * 8 + 16 + BN * 8 + 1024;
     static_assert(SMEM2 <= 227 * 1024, "shared memory budget");
     static PerDeviceFlag attr_flag;
     bool& attr_set = attr_flag.here();
     if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) != cudaSuccess) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES2, 2, 1, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2) != cudaSuccess) {
             snprintf(g_gemm_err, sizeof(g_gemm_err), "cudaFuncSetAttribute (pair): %s", cudaGetErrorString(cudaGetLastError()));
             return -20;
         }
@@ -1566,7 +1608,7 @@ static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
     attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES2, 2, 1, FEAT>, op->mapA0, op->mapA1, op->mapBh, op->mapBL, op->mapA2, op->mapA3, p);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_gemm_err, sizeof(g_gemm_err), "gemm launch (pair): %s", cudaGetErrorString(e));
@@ -1590,22 +1632,34 @@ int gemm_launch(const GemmOp* op, cudaStream_t stream) {
     const int kb_per_tile = (p.num_kb + p.splits - 1) / (p.splits > 0 ? p.splits : 1);
     const bool light = light_max_kb > 0 && op->cluster != 2 && op->BN <= 128 && kb_per_tile <= light_max_kb &&
                        !(p.flags & GEMM_W_BLOCKED);
+    const bool feat = p.ln_stats != nullptr || p.stats_out != nullptr;  // folded LayerNorm / row statistics instantiation
     int r;
-    if (light) {
+    if (light && !feat) {
         switch (op->BN) {
             case 32: r = launch_light<32, 4>(op, stream); break;
             case 64: r = launch_light<64, 4>(op, stream); break;
             default: r = launch_light<128, 3>(op, stream); break;
         }
-    } else
-    switch (op->BN) {
-        case 32: r = launch_cfg<32, 8, 8>(op, stream); break;
-        case 64: r = launch_cfg<64, 8, 8>(op, stream); break;
-        case 128: r = launch_cfg<128, 6, 8>(op, stream); break;
-        case 160: r = launch_cfg<160, 5, 7>(op, stream); break;
-        case 192: r = launch_cfg<192, 5, 7>(op, stream); break;
-        case 320: r = launch_pair_only<320, 6>(op, stream); break;
-        default: r = launch_cfg<256, 4, 6>(op, stream); break;
+    } else if (feat) {
+        switch (op->BN) {
+            case 32: r = launch_cfg<32, 8, 8, 1>(op, stream); break;
+            case 64: r = launch_cfg<64, 8, 8, 1>(op, stream); break;
+            case 128: r = launch_cfg<128, 6, 8, 1>(op, stream); break;
+            case 160: r = launch_cfg<160, 5, 7, 1>(op, stream); break;
+            case 192: r = launch_cfg<192, 5, 7, 1>(op, stream); break;
+            case 320: r = launch_pair_only<320, 6, 1>(op, stream); break;
+            default: r = launch_cfg<256, 4, 6, 1>(op, stream); break;
+        }
+    } else {
+        switch (op->BN) {
+            case 32: r = launch_cfg<32, 8, 8, 0>(op, stream); break;
+            case 64: r = launch_cfg<64, 8, 8, 0>(op, stream); break;
+            case 128: r = launch_cfg<128, 6, 8, 0>(op, stream); break;
+            case 160: r = launch_cfg<160, 5, 7, 0>(op, stream); break;
+            case 192: r = launch_cfg<192, 5, 7, 0>(op, stream); break;
+            case 320: r = launch_pair_only<320, 6, 0>(op, stream); break;
+            default: r = launch_cfg<256, 4, 6, 0>(op, stream); break;
+        }
     }
     if (r) return r;
     if (p.splits > 1 && !splitk_fused(op)) {

@@ -50,6 +50,8 @@ struct GemmParams {
     int rows_valid;    // conv: bw*bh*bn (<= 128) rows of the tile that map to pixels
     int cblocks0;      // 64-channel blocks (per tap) that come from source 0
     int cblocks;       // 64-channel blocks per tap (source 0 + source 1); linear: == num_kb
+    int sc_blocks0;    // conv3x3 + fused 1x1 shortcut: 64-channel blocks of the shortcut's first source (after the 9 taps)
+    int sc_blocks;     //   ... of both shortcut sources; num_kb = 9 * cblocks + sc_blocks
     int splits;        // split-K factor; > 1 writes fp32 partials to workspace; the last-arriving CTA of a tile sums them and
                        // runs the epilogue (tile_counters), or a finalize kernel does (tile_counters == nullptr)
     int nz1, nz2;      // batch extents (heads, samples); grid.z = nz1 * nz2 * splits
@@ -91,6 +93,7 @@ struct GemmParams {
 
 struct GemmOp {
     CUtensorMap mapA0, mapA1, mapB;
+    CUtensorMap mapA2, mapA3;  // conv3x3 with a fused 1x1 shortcut: sources of the shortcut (centre tap); == mapA0 otherwise
     CUtensorMap mapBh;  // B map with a BN/2-row box: each CTA of a CTA pair fetches its half of the weight tile
     CUtensorMap mapBL;  // B map of the ragged last n-tile (box rows = n_last, or n_last/2 in pair mode); == mapB / mapBh if none
     int cluster;        // 1 or 2
@@ -111,8 +114,12 @@ int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __ha
                       const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked = 0);
 // 3x3/s1/p1 conv over NHWC activations: sources (Nimg,H,W,C0) and optional (Nimg,H,W,C1), C0,C1 % 64 == 0;
 // Wt [Cout, 9*(C0+C1)] with k = (ky*3+kx)*(C0+C1) + c.
+// Optional fused 1x1 convolution over other sources S0 (Nimg,H,W,CS0) [| S1 (Nimg,H,W,CS1)] of the same spatial extent
+// (the conv_shortcut of a ResnetBlock2D, computed as extra k-blocks at the centre tap instead of a separate launch plus a
+// residual read): Wt is then [Cout, 9*(C0+C1) + CS0 + CS1] with the shortcut weights appended along K.
 int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, int C1, int Nimg, int H, int W,
-                       const __half* Wt, int Cout, int BN, int splits, int w_blocked = 0);
+                       const __half* Wt, int Cout, int BN, int splits, int w_blocked = 0, const __half* S0 = nullptr,
+                       int CS0 = 0, const __half* S1 = nullptr, int CS1 = 0);
 // Batched product over (z1 in [0,nz1), z2 in [0,nz2)):  D_z[M,N] = A_z[M,K] * B_z^T
 //   A_z = A + z1*a_zs1 + z2*a_zs2 (row stride lda);  K-major B_z[N,K] = B + z1*b_zs1 + z2*b_zs2 (row stride ldb),
 //   or with b_mn: B_z[K,N] row-major (row stride ldb).  All strides in elements, multiples of 8.

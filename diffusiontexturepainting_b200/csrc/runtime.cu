@@ -332,21 +332,39 @@ struct Builder {
         int cout = 0, kk = 0;
         const __half* W = W16(w_name, &cout, &kk);
         if (!W) return;
+        conv3x3_raw(a0, a1, W, cout, kk, prefix + w_name, bias, res, ldr, out, ldc, flags, hw_out, Act{}, Act{});
+    }
+    // same with an explicit weight matrix [cout, kk] and an optional fused 1x1 shortcut over s0 [| s1] (gemm_tc.h)
+    void conv3x3_raw(const Act& a0, const Act& a1, const __half* W, int cout, int kk, const std::string& what,
+                     const float* bias, const __half* res, int ldr, void* out, int ldc, int flags, int hw_out,
+                     const Act& s0, const Act& s1) {
+        if (!ok) return;
         const int C = a0.C + (a1.p ? a1.C : 0);
-        if (kk != 9 * C) {
-            fail("conv weight '" + prefix + w_name + "' has K=" + std::to_string(kk) + ", expected " +
-                 std::to_string(9 * C));
+        const int CS0 = s0.p ? s0.C : 0, CS1 = s1.p ? s1.C : 0;
+        if (kk != 9 * C + CS0 + CS1) {
+            fail("conv weight '" + what + "' has K=" + std::to_string(kk) + ", expected " +
+                 std::to_string(9 * C + CS0 + CS1));
             return;
         }
         GemmOp probe, op;
-        if (gemm_setup_conv3x3(&probe, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, 128, 1)) {
+        if (gemm_setup_conv3x3(&probe, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, 128, 1, 0, s0.p, CS0,
+                               s1.p, CS1)) {
             fail(std::string("conv setup: ") + gemm_last_error());
             return;
         }
         int BN, splits;
         gemm_pick_config(probe.grid_m, cout, probe.p.num_kb,
                          flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
-        if (gemm_setup_conv3x3(&op, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, BN, splits)) {
+        if (CS0 > 0) {
+            // no measured entry for the longer K of a fused shortcut: take the tile / split of the plain convolution
+            int bn0 = 0, sp0 = 0;
+            gemm_pick_config(probe.grid_m, cout, 9 * (C / 64),
+                             flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &bn0, &sp0);
+            BN = bn0;
+            splits = sp0;
+        }
+        if (gemm_setup_conv3x3(&op, a0.p, a0.C, a1.p, a1.p ? a1.C : 0, a0.N, a0.H, a0.W, W, cout, BN, splits, 0, s0.p, CS0,
+                               s1.p, CS1)) {
             fail(std::string("conv setup: ") + gemm_last_error());
             return;
         }
@@ -357,7 +375,7 @@ struct Builder {
         op.p.ldc = ldc > 0 ? ldc : cout;
         op.p.flags |= flags;
         op.p.hw_out = hw_out;
-        push_gemm(op, "conv3x3");
+        push_gemm(op, CS0 > 0 ? "conv3x3+shortcut" : "conv3x3");
     }
     Act conv3x3(const Act& a0, const Act& a1, const std::string& p, const float* bias_override, const __half* res) {
         int cout = 0;
@@ -566,6 +584,22 @@ struct Builder {
         const int cout = n2.C;
         Act sc;
         const __half* scp = x.p;
+        if (e.find(prefix + p + ".conv_shortcut.weight") && e.opt_fuse_shortcut_ && (x.C % 64) == 0 &&
+            (!skip.p || (skip.C % 64) == 0)) {
+            // conv_shortcut (1x1 over x [| skip]) rides along conv2 as extra k-blocks at the centre tap: one launch and one
+            // fp16 round trip of the shortcut activation less, and the sum is taken in the fp32 accumulator
+            const Engine::FusedShortcut* f = e.fused_shortcut(prefix + p, cout, cin);
+            if (!f) {
+                fail(e.err_);
+                return Act{};
+            }
+            Act out = like(x, cout);
+            if (ok)
+                conv3x3_raw(n2, Act{}, f->W, cout, 9 * cout + cin, prefix + p + ".conv2+conv_shortcut", f->bias, nullptr, 0,
+                            out.p, cout, 0, 0, x, skip);
+            release(n2);
+            return out;
+        }
         if (e.find(prefix + p + ".conv_shortcut.weight")) {
             sc = like(x, cout);
             int r = 0, c = 0;
@@ -665,6 +699,36 @@ int Engine::grow_arena(size_t bytes) {
     g_infer_.key.clear();
     g_stamp_.key.clear();
     return ensure_arena();
+}
+
+const Engine::FusedShortcut* Engine::fused_shortcut(const std::string& prefix, int cout, int cin) {
+    auto it = fused_sc_.find(prefix);
+    if (it != fused_sc_.end()) return &it->second;
+    const WT* w2 = find(prefix + ".conv2.weight");
+    const WT* ws = find(prefix + ".conv_shortcut.weight");
+    const WT* b2 = find(prefix + ".conv2.bias");
+    const WT* bs = find(prefix + ".conv_shortcut.bias");
+    if (!w2 || !ws || !b2 || !bs || w2->dtype != 1 || ws->dtype != 1 || w2->shape.size() != 2 || ws->shape.size() != 2 ||
+        w2->shape[0] != cout || w2->shape[1] != 9LL * cout || ws->shape[0] != cout || ws->shape[1] != cin ||
+        b2->host.size() != static_cast<size_t>(cout) || bs->host.size() != static_cast<size_t>(cout)) {
+        fail("fused shortcut: unexpected conv2 / conv_shortcut tensors under '" + prefix + "'");
+        return nullptr;
+    }
+    const size_t K2 = 9 * static_cast<size_t>(cout), KT = K2 + cin;
+    FusedShortcut f;
+    f.W = static_cast<__half*>(persistent(static_cast<size_t>(cout) * KT * 2, false));
+    f.bias = static_cast<float*>(persistent(static_cast<size_t>(cout) * 4, false));
+    if (!f.W || !f.bias) return nullptr;
+    std::vector<float> bsum(cout);
+    for (int i = 0; i < cout; ++i) bsum[i] = b2->host[i] + bs->host[i];
+    if (cudaMemcpy2D(f.W, KT * 2, w2->dev, K2 * 2, K2 * 2, cout, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+        cudaMemcpy2D(f.W + K2, KT * 2, ws->dev, static_cast<size_t>(cin) * 2, static_cast<size_t>(cin) * 2, cout,
+                     cudaMemcpyDeviceToDevice) != cudaSuccess ||
+        cudaMemcpy(f.bias, bsum.data(), static_cast<size_t>(cout) * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail("fused shortcut: weight concatenation failed");
+        return nullptr;
+    }
+    return &fused_sc_.emplace(prefix, f).first->second;
 }
 
 int Engine::check_device_error() {
@@ -852,6 +916,7 @@ int Engine::finalize_weights() {
     cond_plan_.clear();
     temb_dirty_ = true;
     cond_set_ = false;
+    fused_sc_.clear();
     if (prepare_ln_fold()) return -1;
     finalized_ = true;
     return 0;
@@ -918,6 +983,10 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
     // each into one plugin op in front of the GEMM, models.py:304-365): the producer of h emits per-row partial sums, the
     // consumer multiplies the raw rows by gamma-scaled weights and normalises in its epilogue. Needs C % 32 == 0.
     const bool fl = e.fold_ln() && (C % 32) == 0 && e.fold_cross();
+    // The GEGLU contraction is epilogue-bound at the wide levels (6.5 tiles of 128 x 256 per CTA at 12 288 rows): there the
+    // folded epilogue costs more than the LayerNorm kernel it removes (measured +12 us vs -10.5 us), so norm3 is folded
+    // only below fold_ln_ff_rows rows (norm1 / norm2 are folded everywhere: QKV +6 us / scores +2.5 us vs -10.5 us each)
+    const bool fl3 = fl && rows <= e.fold_ln_ff_rows();
     float2* st = fl ? static_cast<float2*>(b.raw(static_cast<size_t>(rows) * (C / 32) * sizeof(float2))) : nullptr;
     Act n = b.groupnorm(x, Act{}, p + ".norm", 1e-6f, 0);
     Act h = b.like(x, C);
@@ -994,7 +1063,7 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
             g.M = static_cast<int>(grp_rows); g.N = C; g.K = HP; g.nz1 = 3;
             g.out = h.p; g.ldc = C; g.out_zs1 = grp_rows * C;
             g.bias = b.F32(t + ".attn2.to_out.0.bias");
-            g.res = h.p; g.ldr = C; g.res_zs1 = grp_rows * C; g.label = "cross_out"; g.stats_out = st;
+            g.res = h.p; g.ldr = C; g.res_zs1 = grp_rows * C; g.label = "cross_out"; g.stats_out = fl3 ? st : nullptr;
             b.bmm(g);
         }
         b.release(P);
@@ -1023,22 +1092,22 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.release(att);
     }
     // GEGLU feed-forward
-    if (!fl) {
+    if (!fl3) {
         tmp = b.like(x, C);
         b.layernorm(h, t + ".norm3", tmp.p);
     }
     Act g = b.like(x, 4 * C);
     {
         Lin l;
-        l.A0 = fl ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = fl ? e.ln(tf).ff1_w : b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
-        l.bias = fl ? e.ln(tf).ff1_b : b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
-        if (fl) {
+        l.A0 = fl3 ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.W = fl3 ? e.ln(tf).ff1_w : b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
+        l.bias = fl3 ? e.ln(tf).ff1_b : b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
+        if (fl3) {
             l.ln_stats = st; l.ln_colsum = e.ln(tf).ff1_cs; l.ln_C = C;
         }
         b.linear(l);
     }
-    if (!fl) b.release(tmp);
+    if (!fl3) b.release(tmp);
     {
         Lin l;
         l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
@@ -2066,6 +2135,22 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "fold_cross") {
         opt_fold_cross_ = value;
+        unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fuse_shortcut") {
+        opt_fuse_shortcut_ = value;
+        unet_plan_.clear();
+        vae_enc_plan_.clear();
+        vae_dec_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fold_ln_ff_rows") {
+        opt_fold_ln_ff_rows_ = value;
         unet_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();

@@ -150,8 +150,16 @@ class Engine {
     int check_device_error();
     int grow_arena(size_t bytes);
     bool fold_cross() const { return opt_fold_cross_ != 0; }
+    // conv2 and conv_shortcut of a ResnetBlock2D concatenated along K ([cout, 9*cout + cin], bias = conv2.bias +
+    // conv_shortcut.bias): built on first use, cached per resnet prefix
+    struct FusedShortcut {
+        __half* W = nullptr;
+        float* bias = nullptr;
+    };
+    const FusedShortcut* fused_shortcut(const std::string& prefix, int cout, int cin);
     bool fold_ln() const { return opt_fold_ln_ != 0 && !ln_.empty(); }
     const LnFold& ln(int i) const { return ln_[i]; }
+    long long fold_ln_ff_rows() const { return opt_fold_ln_ff_rows_; }
     int tf_index(const std::string& prefix) const {
         for (size_t i = 0; i < tf_names_.size(); ++i)
             if (tf_names_[i] == prefix) return static_cast<int>(i);
@@ -217,7 +225,10 @@ class Engine {
     std::vector<__half*> wout_;      // per layer: (3, C, heads*16)  Wo_h V_h^T
     int opt_fold_cross_ = 1;
     std::vector<LnFold> ln_;
+    std::unordered_map<std::string, FusedShortcut> fused_sc_;
+    int opt_fuse_shortcut_ = 1;
     int opt_fold_ln_ = 1;
+    int opt_fold_ln_ff_rows_ = 1024;  // norm3 -> FF1 folding only for activations of at most this many rows
     int prepare_ln_fold();
     std::vector<std::string> tf_names_;  // transformer prefixes in execution order
     bool cond_set_ = false;

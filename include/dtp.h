@@ -66,6 +66,11 @@ int dtp_op_linear(const void* A0, int lda0, int K0, const void* A1, int lda1, in
 int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int H, int W, const void* Wt, int Cout,
                    const float* bias, const void* residual, int ldr, void* out, int ldc, int flags, float alpha,
                    int hw_out, int BN, int splits, void* stream);
+/* ResnetBlock2D tail in one contraction: out = conv3x3(A0) + conv1x1([S0 | S1]) + bias. A0 (Nimg,H,W,C0), shortcut sources
+ * S0 (Nimg,H,W,CS0) and optional S1 (Nimg,H,W,CS1) NHWC f16; Wt [Cout, 9*C0 + CS0 + CS1] (conv2 rows with the conv_shortcut
+ * rows appended along K), bias = conv2.bias + conv_shortcut.bias (diffusers ResnetBlock2D.forward: output = shortcut(x) + h) */
+int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, const void* S1, int CS1, int Nimg, int H, int W,
+                            const void* Wt, int Cout, const float* bias, void* out, int BN, int splits, void* stream);
 /* batched D_z = alpha * A_z * B_z^T over z = (z1 < nz1, z2 < nz2); b_mn: B_z given as [K,N] row-major */
 int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
                long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
@@ -159,7 +164,12 @@ int dtp_vae_decode(dtp_handle* h, int B, int R, const float* latents, float* ima
 /* one UNet evaluation at schedule index `step`: sample (3B,9,h,h) f32 -> eps (3B,4,h,h) f32 */
 int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const float* reserved0, const float* reserved1,
                      int step, float* eps_out, void* stream);
-/* counters: "launches" (kernels launched by this engine so far), "stamps", "arena_peak", "arena_bytes" */
+/* counters: "launches" (kernels launched by this engine so far), "stamps", "arena_peak", "arena_bytes", "graph_launches",
+ * "unet_plan_ops", "device", "stage_us_<k>" / "stage_n_<k>" (k = 0..5: canvas_preprocess, vae_encoder, unet, latent_step,
+ * vae, composite; device time and count accumulated since dtp_set_option("stage_timers", 1)).
+ * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fold_ln" (LayerNorm folded into the consuming
+ * contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside conv2), "flash", "profile" (per-op events),
+ * "stage_timers", "nvtx" (NVTX ranges per stage), "arena_mib" (grow the activation arena to at least this size). */
 long long dtp_get_counter(dtp_handle* h, const char* name);
 int dtp_set_option(dtp_handle* h, const char* name, int value);
 /* after dtp_set_option(h, "profile", 1): CSV of device time per distinct op (label, calls, microseconds), slowest first */

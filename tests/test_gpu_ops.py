@@ -167,6 +167,29 @@ def test_conv3x3_wide_pair_tile(n, H, W, cin, cout, splits):
     assert rel_l2(out, conv_ref(x, w, cin, b) + r.float()) < 2e-3
 
 
+@pytest.mark.parametrize("n,H,W,c2,cs0,cs1,cout,BN,splits", [(3, 16, 16, 128, 64, 0, 128, 0, 1), (3, 8, 8, 256, 128, 128, 256, 128, 3),
+                                                              (3, 32, 32, 64, 64, 128, 320, 320 | PAIR, 1), (2, 16, 16, 128, 192, 0, 128, 64, 2),
+                                                              (3, 64, 64, 320, 320, 320, 320, 0, 1)])
+def test_conv3x3_with_fused_shortcut(n, H, W, c2, cs0, cs1, cout, BN, splits):
+    """conv2 + conv_shortcut of a ResnetBlock2D as ONE contraction (shortcut = extra k-blocks at the centre tap)"""
+    L = nat.lib()
+    x = h(rnd(n, H, W, c2))
+    s0 = h(rnd(n, H, W, cs0, seed=1))
+    s1 = h(rnd(n, H, W, cs1, seed=2)) if cs1 else None
+    w2 = h(rnd(cout, 9 * c2, scale=(9 * c2) ** -0.5, seed=3))
+    ws = h(rnd(cout, cs0 + cs1, scale=(cs0 + cs1) ** -0.5, seed=4))
+    wt = torch.cat([w2, ws], 1).contiguous()
+    bias = rnd(cout, seed=5)
+    out = torch.empty(n, H, W, cout, device=DEV, dtype=torch.float16)
+    rc = L.dtp_op_conv3x3_shortcut(nat.ptr(x), c2, nat.ptr(s0), cs0, nat.ptr(s1), cs1, n, H, W, nat.ptr(wt), cout,
+                                   nat.ptr(bias), nat.ptr(out), BN, splits, nat.stream_ptr())
+    nat.check_op(rc, "conv3x3_shortcut")
+    torch.cuda.synchronize()
+    s = torch.cat([s0, s1], 3) if cs1 else s0
+    ref = conv_ref(x, w2, c2) + s.float() @ ws.float().t() + bias
+    assert rel_l2(out, ref) < 2e-3
+
+
 def test_conv3x3_small_cout_f32_nchw():
     n, H, W, cin, cout = 3, 16, 16, 320, 4
     x, w, b = h(rnd(n, H, W, cin)), h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5)), rnd(cout)

@@ -291,7 +291,10 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     eng.set_option("fold_ln", 1)
     outs["ln_folded"] = model.generate(canvas, init_latents=lat, **settings).clone()
     assert eng.counter("unet_plan_ops") < n_unfolded  # three launches fewer per transformer block
-    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded"):
+    eng.set_option("fuse_shortcut", 0)   # conv_shortcut as its own 1x1 contraction + residual read in conv2
+    outs["shortcut_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("fuse_shortcut", 1)
+    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
