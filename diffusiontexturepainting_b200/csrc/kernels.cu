@@ -737,9 +737,11 @@ __global__ void __launch_bounds__(256) ln_fold_weights_kernel(const __half* __re
     float cs = 0.0f, bs = 0.0f;
     for (int k = lane; k < K; k += 32) {
         const float w = __half2float(W[static_cast<long long>(n) * ldw + k]);
-        const __half wp = __float2half_rn(w * __ldg(gamma + k));
-        Wout[static_cast<long long>(n) * ldw + k] = wp;
-        cs += __half2float(wp);
+        if (Wout != nullptr) {  // (gamma == nullptr with Wout == nullptr: plain bias_out = bias_in + W beta)
+            const __half wp = __float2half_rn(w * __ldg(gamma + k));
+            Wout[static_cast<long long>(n) * ldw + k] = wp;
+            cs += __half2float(wp);
+        }
         bs = fmaf(w, __ldg(beta + k), bs);
     }
     cs = warp_sum(cs);

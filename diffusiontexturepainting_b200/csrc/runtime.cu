@@ -142,6 +142,7 @@ struct Lin {
     const float* ln_colsum = nullptr;
     int ln_C = 0;
     float2* stats_out = nullptr;
+    int tune_kb = 0;  // > 0: look the tile / split configuration up for this many k-blocks (a measured neighbour shape)
 };
 
 struct Builder {
@@ -232,7 +233,8 @@ struct Builder {
         int BN, splits;
         const int kb = (a.K0 + 63) / 64 + (a.A1 ? (a.K1 + 63) / 64 : 0);
         const int mt = static_cast<int>((a.M + 127) / 128);
-        gemm_pick_config(mt, a.N, kb, a.flags | ((mt >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
+        gemm_pick_config(mt, a.N, a.tune_kb > 0 ? a.tune_kb : kb,
+                         a.flags | ((mt >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
         if (gemm_setup_linear(&op, a.A0, a.lda0, a.K0, a.A1, a.lda1, a.K1, static_cast<int>(a.M), a.W, a.ldw, a.N, BN,
                               splits)) {
             fail(std::string("linear setup: ") + gemm_last_error());
@@ -918,7 +920,49 @@ int Engine::finalize_weights() {
     cond_set_ = false;
     fused_sc_.clear();
     if (prepare_ln_fold()) return -1;
+    if (prepare_ff_out()) return -1;
     finalized_ = true;
+    return 0;
+}
+
+// [Wp W2 | Wp] and Wp b2 + bp per transformer layer (runtime.h, FfOut); the product runs on the contraction kernel itself
+int Engine::prepare_ff_out() {
+    ffo_.clear();
+    if (ensure_arena()) return -1;
+    std::vector<FfOut> v(tf_names_.size());
+    Plan plan;
+    Builder b(*this, plan, "unet.");
+    for (size_t i = 0; i < tf_names_.size(); ++i) {
+        const std::string t = tf_names_[i] + ".transformer_blocks.0";
+        int C = 0, k2 = 0, cp = 0, kp = 0;
+        const __half* W2 = b.W16(t + ".ff.net.2.weight", &C, &k2);
+        const __half* Wp = b.W16(tf_names_[i] + ".proj_out.weight", &cp, &kp);
+        const float* b2 = b.F32(t + ".ff.net.2.bias");
+        const float* bp = b.F32(tf_names_[i] + ".proj_out.bias");
+        if (!b.ok) {
+            b.ok = true;  // a checkpoint without these tensors simply keeps the two-launch tail
+            return 0;
+        }
+        if (k2 != 4 * C || cp != C || kp != C || (C % 8) != 0) return 0;
+        FfOut& f = v[i];
+        f.W = static_cast<__half*>(persistent(static_cast<size_t>(C) * 5 * C * 2, false));
+        f.bias = static_cast<float*>(persistent(static_cast<size_t>(C) * 4, false));
+        if (!f.W || !f.bias) return -1;
+        Builder::Bmm g;  // (Wp W2)[n, k4] = sum_c Wp[n, c] W2[c, k4]: W2 consumed as an MN-major B operand
+        g.A = Wp; g.lda = C; g.B = W2; g.ldb = 4 * C; g.b_mn = 1;
+        g.M = C; g.N = 4 * C; g.K = C; g.out = f.W; g.ldc = 5 * C; g.label = "ff_out_fold";
+        b.bmm(g);
+        if (!b.ok) return -1;
+        if (cudaMemcpy2DAsync(f.W + 4 * C, static_cast<size_t>(5) * C * 2, Wp, static_cast<size_t>(C) * 2,
+                              static_cast<size_t>(C) * 2, C, cudaMemcpyDeviceToDevice, 0) != cudaSuccess)
+            return fail("ff_out fold: copy failed");
+        if (launch_ln_fold_weights(Wp, C, C, C, nullptr, b2, bp, nullptr, nullptr, f.bias, 0))
+            return fail(std::string("ff_out fold: ") + kernels_last_error());
+    }
+    if (ensure_ws()) return -1;
+    if (plan.run(0, &launches_, nullptr)) return -1;
+    if (cudaStreamSynchronize(0) != cudaSuccess) return fail("ff_out fold: device error");
+    ffo_ = std::move(v);
     return 0;
 }
 
@@ -1108,21 +1152,31 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.linear(l);
     }
     if (!fl3) b.release(tmp);
-    {
-        Lin l;
-        l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
-        l.W = b.W16(t + ".ff.net.2.weight"); l.ldw = 4 * C; l.N = C;
-        l.bias = b.F32(t + ".ff.net.2.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
-        b.linear(l);
-    }
-    b.release(g);
     Act out = b.like(x, C);
-    {
+    if (e.fuse_ff_out()) {
+        // ff.net.2 + residual + proj_out + residual as ONE contraction over [g | h] (runtime.h, FfOut)
         Lin l;
-        l.A0 = h.p; l.lda0 = C; l.K0 = C; l.M = rows;
-        l.W = b.W16(p + ".proj_out.weight"); l.ldw = C; l.N = C;
-        l.bias = b.F32(p + ".proj_out.bias"); l.res = x.p; l.ldr = C; l.out = out.p;
+        l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.A1 = h.p; l.lda1 = C; l.K1 = C; l.M = rows;
+        l.W = e.ffo(tf).W; l.ldw = 5 * C; l.N = C; l.bias = e.ffo(tf).bias;
+        l.res = x.p; l.ldr = C; l.out = out.p; l.tune_kb = 4 * C / 64;
         b.linear(l);
+        b.release(g);
+    } else {
+        {
+            Lin l;
+            l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
+            l.W = b.W16(t + ".ff.net.2.weight"); l.ldw = 4 * C; l.N = C;
+            l.bias = b.F32(t + ".ff.net.2.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
+            b.linear(l);
+        }
+        b.release(g);
+        {
+            Lin l;
+            l.A0 = h.p; l.lda0 = C; l.K0 = C; l.M = rows;
+            l.W = b.W16(p + ".proj_out.weight"); l.ldw = C; l.N = C;
+            l.bias = b.F32(p + ".proj_out.bias"); l.res = x.p; l.ldr = C; l.out = out.p;
+            b.linear(l);
+        }
     }
     b.release(h);
     if (st) b.release_raw(st);
@@ -2135,6 +2189,13 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "fold_cross") {
         opt_fold_cross_ = value;
+        unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fuse_ff_out") {
+        opt_fuse_ff_out_ = value;
         unet_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();

@@ -116,6 +116,14 @@ struct LnFold {
     float *ws_cs = nullptr, *ws_b = nullptr;  // (3, heads*16)
 };
 
+// ff.net.2 and proj_out of a transformer block are two linear maps with nothing but a residual between them:
+//   out = (g W2^T + b2 + h) Wp^T + bp + x = [g | h] [Wp W2 | Wp]^T + (Wp b2 + bp) + x
+// -> one contraction over K = 4C + C with the product weights prepared at finalize_weights (per transformer layer)
+struct FfOut {
+    __half* W = nullptr;  // (C, 5C)
+    float* bias = nullptr;
+};
+
 class Engine {
    public:
     explicit Engine(const dtp_config& cfg);
@@ -159,6 +167,8 @@ class Engine {
     const FusedShortcut* fused_shortcut(const std::string& prefix, int cout, int cin);
     bool fold_ln() const { return opt_fold_ln_ != 0 && !ln_.empty(); }
     const LnFold& ln(int i) const { return ln_[i]; }
+    bool fuse_ff_out() const { return opt_fuse_ff_out_ != 0 && !ffo_.empty(); }
+    const FfOut& ffo(int i) const { return ffo_[i]; }
     long long fold_ln_ff_rows() const { return opt_fold_ln_ff_rows_; }
     int tf_index(const std::string& prefix) const {
         for (size_t i = 0; i < tf_names_.size(); ++i)
@@ -225,6 +235,9 @@ class Engine {
     std::vector<__half*> wout_;      // per layer: (3, C, heads*16)  Wo_h V_h^T
     int opt_fold_cross_ = 1;
     std::vector<LnFold> ln_;
+    std::vector<FfOut> ffo_;
+    int opt_fuse_ff_out_ = 1;
+    int prepare_ff_out();
     std::unordered_map<std::string, FusedShortcut> fused_sc_;
     int opt_fuse_shortcut_ = 1;
     int opt_fold_ln_ = 1;

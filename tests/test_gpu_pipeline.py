@@ -294,7 +294,10 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     eng.set_option("fuse_shortcut", 0)   # conv_shortcut as its own 1x1 contraction + residual read in conv2
     outs["shortcut_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
     eng.set_option("fuse_shortcut", 1)
-    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate"):
+    eng.set_option("fuse_ff_out", 0)   # ff.net.2 and proj_out as two contractions
+    outs["ff_out_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("fuse_ff_out", 1)
+    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
