@@ -29,6 +29,7 @@ struct FlashParams {
     __half* out;
     int ldo;
     long long o_bs;
+    int stagger;  // two-warpgroup kernel: warpgroup 1 starts its first block half a period after warpgroup 0 (DTP_FLASH_STAGGER)
 };
 
 __device__ __forceinline__ void fa_wait(uint64_t* bar, uint32_t parity) {
@@ -42,6 +43,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two lanes per instruction; nvcc does not form these on its own
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+    unsigned long long av, bv, cv, dv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cv) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dv) : "l"(av), "l"(bv), "l"(cv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dv));
+}
+__device__ __forceinline__ void fadd2(float& acc0, float& acc1, float a0, float a1) {
+    unsigned long long av, cv, dv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(acc0), "f"(acc1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(dv) : "l"(av), "l"(cv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc0), "=f"(acc1) : "l"(dv));
 }
 // three-input maximum (FMNMX3 on sm_100): halves the instruction count of the row-maximum pass
 __device__ __forceinline__ float max3(float a, float b, float c) {
@@ -493,6 +510,10 @@ __global__ void __launch_bounds__(384, 1)
         const uint32_t sw16 = static_cast<uint32_t>(sw) << 4;
         const float sc = p.scale_log2;
         for (int j = 0; j < nblk; ++j) {
+            // The two warpgroups share the SM's MUFU pipe: started together they run their exponential phases at the same
+            // time and idle at the same time. Warpgroup 1 therefore begins its first block only when warpgroup 0 has
+            // finished the exponentials of its first one (one handshake; the half-period offset then persists).
+            if (p.stagger && j == 0 && w == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
             fa_wait(&s_full[w], j & 1);
             tc_fence_after();
             const int kv_valid = min(128, p.seq_kv - j * 128);
@@ -542,14 +563,22 @@ __global__ void __launch_bounds__(384, 1)
             for (int c = 0; c < 128; c += 8) {
                 float e[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(raw[c + i]), sc, neg_m));
-                l0 += (e[0] + e[1]) + (e[2] + e[3]);
-                l1 += (e[4] + e[5]) + (e[6] + e[7]);
+                for (int i = 0; i < 8; i += 2) {
+                    float x0, x1;
+                    ffma2(x0, x1, __uint_as_float(raw[c + i]), __uint_as_float(raw[c + i + 1]), sc, neg_m);
+                    e[i] = ex2_approx(x0);
+                    e[i + 1] = ex2_approx(x1);
+                }
+                fadd2(l0, l1, e[0], e[1]);
+                fadd2(l0, l1, e[2], e[3]);
+                fadd2(l0, l1, e[4], e[5]);
+                fadd2(l0, l1, e[6], e[7]);
                 pk[(c >> 1) + 0] = pack_half2(e[0], e[1]);
                 pk[(c >> 1) + 1] = pack_half2(e[2], e[3]);
                 pk[(c >> 1) + 2] = pack_half2(e[4], e[5]);
                 pk[(c >> 1) + 3] = pack_half2(e[6], e[7]);
             }
+            if (p.stagger && j == 0 && w == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
             if (j > 0) fa_wait(&o_done[w], (j - 1) & 1);  // P buffer free again, O_{j-1} final
             tc_fence_after();
             if (__any_sync(0xffffffffu, need)) {
@@ -960,6 +989,11 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
     p.out = op->out;
     p.ldo = op->ldo;
     p.o_bs = op->o_bs;
+    static const int stagger = []() {
+        const char* e = getenv("DTP_FLASH_STAGGER");
+        return e ? atoi(e) : 1;
+    }();
+    p.stagger = stagger;
     int r;
     static const bool two_wg = []() {
         const char* e = getenv("DTP_FLASH2");
