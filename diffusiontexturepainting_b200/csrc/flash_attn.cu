@@ -29,7 +29,6 @@ struct FlashParams {
     __half* out;
     int ldo;
     long long o_bs;
-    int stagger;  // two-warpgroup kernel: warpgroup 1 starts its first block half a period after warpgroup 0 (DTP_FLASH_STAGGER)
 };
 
 __device__ __forceinline__ void fa_wait(uint64_t* bar, uint32_t parity) {
@@ -510,10 +509,6 @@ __global__ void __launch_bounds__(384, 1)
         const uint32_t sw16 = static_cast<uint32_t>(sw) << 4;
         const float sc = p.scale_log2;
         for (int j = 0; j < nblk; ++j) {
-            // The two warpgroups share the SM's MUFU pipe: started together they run their exponential phases at the same
-            // time and idle at the same time. Warpgroup 1 therefore begins its first block only when warpgroup 0 has
-            // finished the exponentials of its first one (one handshake; the half-period offset then persists).
-            if (p.stagger && j == 0 && w == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
             fa_wait(&s_full[w], j & 1);
             tc_fence_after();
             const int kv_valid = min(128, p.seq_kv - j * 128);
@@ -578,7 +573,6 @@ __global__ void __launch_bounds__(384, 1)
                 pk[(c >> 1) + 2] = pack_half2(e[4], e[5]);
                 pk[(c >> 1) + 3] = pack_half2(e[6], e[7]);
             }
-            if (p.stagger && j == 0 && w == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
             if (j > 0) fa_wait(&o_done[w], (j - 1) & 1);  // P buffer free again, O_{j-1} final
             tc_fence_after();
             if (__any_sync(0xffffffffu, need)) {
@@ -989,11 +983,6 @@ int flash_attn_launch(const FlashOp* op, cudaStream_t st) {
     p.out = op->out;
     p.ldo = op->ldo;
     p.o_bs = op->o_bs;
-    static const int stagger = []() {
-        const char* e = getenv("DTP_FLASH_STAGGER");
-        return e ? atoi(e) : 1;
-    }();
-    p.stagger = stagger;
     int r;
     static const bool two_wg = []() {
         const char* e = getenv("DTP_FLASH2");
