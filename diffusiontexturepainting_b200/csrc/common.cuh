@@ -347,6 +347,52 @@ __device__ __forceinline__ float gelu_erf_lean(float x) {
     return fmaf(hx, copysignf(y, z), hx);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, sm_100): two values per instruction. nvcc never forms these itself;
+// the epilogues are instruction-latency bound (two warps per SM partition), so halving the FP32 instruction count of their
+// element-wise tails is worth writing out by hand. A pair lives in a 64-bit register (lo = first value).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a * gelu_erf(g) for two (a, g) pairs: the same Abramowitz-Stegun erf as gelu_erf_lean, arranged so that everything but
+// the two rcp and two ex2 is a packed instruction: gelu(x) = hx - |hx| * w with hx = x / 2, w = poly(t) t e - 1 = -erf(|z|)
+__device__ __forceinline__ f32x2 geglu2(f32x2 a, f32x2 g) {
+    const f32x2 z = mul2(g, pk2(0.70710678118654752f));
+    const f32x2 az = z & 0x7FFFFFFF7FFFFFFFULL;
+    float d0, d1, q0, q1;
+    upk2(fma2(pk2(0.3275911f), az, pk2(1.0f)), d0, d1);
+    upk2(mul2(mul2(az, az), pk2(-1.4426950408889634f)), q0, q1);
+    const f32x2 t = pk2(rcp_ftz(d0), rcp_ftz(d1));
+    const f32x2 e = pk2(ex2_ftz(q0), ex2_ftz(q1));
+    f32x2 poly = fma2(pk2(1.061405429f), t, pk2(-1.453152027f));
+    poly = fma2(poly, t, pk2(1.421413741f));
+    poly = fma2(poly, t, pk2(-0.284496736f));
+    poly = fma2(poly, t, pk2(0.254829592f));
+    const f32x2 w = fma2(mul2(poly, t), e, pk2(-1.0f));
+    const f32x2 hx = mul2(g, pk2(0.5f));
+    const f32x2 nahx = hx | 0x8000000080000000ULL;  // -|hx|
+    return mul2(a, fma2(nahx, w, hx));
+}
 __device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane per instruction. A lane that writes its 64..128

@@ -685,21 +685,30 @@ __global__ void __launch_bounds__(320, OCC)
                         const float* bc = sbias + cc;
                         if (ln_on) {
                             const float* cs = scolsum + cc;
+                            const f32x2 r2 = pk2(ln_r), nm2 = pk2(ln_nm);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], ln_r, fmaf(ln_nm, cs[i], bc[i]));
+                            for (int i = 0; i < 32; i += 2)
+                                upk2(fma2(pk2(v[i], v[i + 1]), r2, fma2(nm2, pk2(cs[i], cs[i + 1]), pk2(bc[i], bc[i + 1]))), v[i],
+                                     v[i + 1]);
                         } else if (col_bias) {
+                            const f32x2 al2 = pk2(p.alpha);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], p.alpha, bc[i]);
+                            for (int i = 0; i < 32; i += 2)
+                                upk2(fma2(pk2(v[i], v[i + 1]), al2, pk2(bc[i], bc[i + 1])), v[i], v[i + 1]);
                         } else {
+                            const f32x2 al2 = pk2(p.alpha);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+                            for (int i = 0; i < 32; i += 2) upk2(mul2(pk2(v[i], v[i + 1]), al2), v[i], v[i + 1]);
                         }
                         if (row >= 0) {
                             if (p.flags & EPI_GEGLU) {
                                 uint32_t o[8];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    o[i] = pack_half2(v[2 * i] * gelu_erf_lean(v[16 + 2 * i]), v[2 * i + 1] * gelu_erf_lean(v[17 + 2 * i]));
+                                for (int i = 0; i < 8; ++i) {
+                                    float o0, o1;
+                                    upk2(geglu2(pk2(v[2 * i], v[2 * i + 1]), pk2(v[16 + 2 * i], v[17 + 2 * i])), o0, o1);
+                                    o[i] = pack_half2(o0, o1);
+                                }
                                 __half* out = reinterpret_cast<__half*>(p.out) + out_off + static_cast<long long>(row) * p.ldc +
                                               ((c.n0 + cc) >> 1);
                                 st_global_v8(out, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
@@ -711,8 +720,8 @@ __global__ void __launch_bounds__(320, OCC)
 #pragma unroll
                                         for (int j = 0; j < 4; ++j) {
                                             const float2 f = __half22float2(h2[j]);
-                                            v[8 * i + 2 * j] += f.x;
-                                            v[8 * i + 2 * j + 1] += f.y;
+                                            upk2(add2(pk2(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]), pk2(f.x, f.y)), v[8 * i + 2 * j],
+                                                 v[8 * i + 2 * j + 1]);
                                         }
                                     }
                                     if (it + RD < IT && it + RD < n_mine) {
