@@ -1341,6 +1341,10 @@ static bool tuned_lookup(int mtiles, int N, int num_kb, int flags, int* BN, int*
     return false;
 }
 
+bool gemm_tuned_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
+    return tuned_lookup(mtiles, N, num_kb, flags, BN, splits);
+}
+
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits) {
     if (tuned_lookup(mtiles, N, num_kb, flags, BN, splits)) return;
     // Cost model (SM cycles) of the persistent kernel, searched over (BN, split-K):

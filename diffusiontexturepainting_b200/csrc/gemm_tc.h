@@ -134,6 +134,8 @@ void gemm_prepare_splitk();
 size_t gemm_workspace_bytes(const GemmOp* op);
 // heuristic tile / split selection for a problem with `mtiles` 128-row tiles
 void gemm_pick_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits);
+// true (and *BN / *splits set) when the measured table holds this exact problem shape
+bool gemm_tuned_config(int mtiles, int N, int num_kb, int flags, int* BN, int* splits);
 const char* gemm_last_error();
 // true when linear / conv problems with >= 2 m-tiles run as 2-CTA clusters (DTP_CLUSTER=0 disables)
 bool gemm_cluster_enabled();

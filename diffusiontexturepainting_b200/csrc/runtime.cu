@@ -233,8 +233,9 @@ struct Builder {
         int BN, splits;
         const int kb = (a.K0 + 63) / 64 + (a.A1 ? (a.K1 + 63) / 64 : 0);
         const int mt = static_cast<int>((a.M + 127) / 128);
-        gemm_pick_config(mt, a.N, a.tune_kb > 0 ? a.tune_kb : kb,
-                         a.flags | ((mt >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
+        const int hint = a.flags | ((mt >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0);
+        if (!gemm_tuned_config(mt, a.N, kb, hint, &BN, &splits))  // exact shape measured? else a measured neighbour / the model
+            gemm_pick_config(mt, a.N, a.tune_kb > 0 ? a.tune_kb : kb, hint, &BN, &splits);
         if (gemm_setup_linear(&op, a.A0, a.lda0, a.K0, a.A1, a.lda1, a.K1, static_cast<int>(a.M), a.W, a.ldw, a.N, BN,
                               splits)) {
             fail(std::string("linear setup: ") + gemm_last_error());
@@ -357,8 +358,8 @@ struct Builder {
         int BN, splits;
         gemm_pick_config(probe.grid_m, cout, probe.p.num_kb,
                          flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &BN, &splits);
-        if (CS0 > 0) {
-            // no measured entry for the longer K of a fused shortcut: take the tile / split of the plain convolution
+        if (CS0 > 0 && !gemm_tuned_config(probe.grid_m, cout, probe.p.num_kb, flags, &BN, &splits)) {
+            // no measured entry for the longer K of this fused shortcut: take the tile / split of the plain convolution
             int bn0 = 0, sp0 = 0;
             gemm_pick_config(probe.grid_m, cout, 9 * (C / 64),
                              flags | ((probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0), &bn0, &sp0);

@@ -104,6 +104,28 @@ def sweep_conv(n, H, Wd, cin, cout):
            2.0 * n * H * Wd * cout * 9 * cin)
 
 
+def sweep_conv_sc(n, H, Wd, c2, cs, cout):
+    """conv2 + fused 1x1 shortcut (dtp_op_conv3x3_shortcut): K = 9 * c2 + cs"""
+    nbuf = ring(cout * (9 * c2 + cs) * 2)
+    x = torch.randn(n, H, Wd, c2, device=dev).half()
+    sx = torch.randn(n, H, Wd, cs, device=dev).half()
+    ws = [torch.randn(cout, 9 * c2 + cs, device=dev).half() for _ in range(nbuf)]
+    out = torch.empty(n, H, Wd, cout, device=dev, dtype=torch.float16)
+    bias = torch.randn(cout, device=dev)
+    res = {}
+
+    def mk(BN, sp):
+        def f(i):
+            nat.check_op(L.dtp_op_conv3x3_shortcut(nat.ptr(x), c2, nat.ptr(sx), cs, None, 0, n, H, Wd, nat.ptr(ws[i % nbuf]), cout,
+                                                   nat.ptr(bias), nat.ptr(out), BN, sp, nat.stream_ptr()))
+        return f
+    for BN, sp in configs(n * H * Wd, cout, 9 * c2 + cs):
+        res[(BN, sp)] = timeit(mk(BN, sp), nbuf)
+    auto = timeit(mk(0, 1), nbuf)
+    report(f"conv3x3sc n={n} {H}x{Wd} c2={c2} cs={cs} cout={cout} (M={n*H*Wd} K={9*c2+cs})", res, auto,
+           2.0 * n * H * Wd * cout * (9 * c2 + cs))
+
+
 CSV = open(os.path.join(ROOT, "gpurun_out", "sweep_all.csv"), "a") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None
 
 
@@ -152,6 +174,14 @@ if __name__ == "__main__":
                     (1, 64, 64, 512, 512), (2, 64, 64, 512, 512), (1, 256, 256, 512, 256), (1, 256, 256, 512, 512),
                     (1, 512, 512, 256, 256)]:
             sweep_conv(*shp)
+    if which in ("all", "r2"):  # shapes introduced by the round-2 fusions: ff.net.2 + proj_out (K = 5C), conv2 + conv_shortcut
+        for shp in [(12288, 320, 1600), (3072, 640, 3200), (768, 1280, 6400), (192, 1280, 6400)]:
+            sweep_linear(*shp)
+        for shp in [(3, 64, 64, 320, 960, 320), (3, 64, 64, 320, 640, 320), (3, 32, 32, 640, 320, 640),
+                    (3, 32, 32, 640, 1920, 640), (3, 32, 32, 640, 1280, 640), (3, 32, 32, 640, 960, 640),
+                    (3, 16, 16, 1280, 640, 1280), (3, 16, 16, 1280, 2560, 1280), (3, 16, 16, 1280, 1920, 1280),
+                    (3, 8, 8, 1280, 2560, 1280)]:
+            sweep_conv_sc(*shp)
     if which in ("all", "vae"):
         for shp in [(2, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:
             sweep_conv(*shp)
