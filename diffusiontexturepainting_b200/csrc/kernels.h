@@ -47,6 +47,25 @@ int flash_attn_setup(FlashOp* op, const __half* q, const __half* k, const __half
 int flash_attn_launch(const FlashOp* op, cudaStream_t st);
 const char* flash_last_error();
 
+// Fused image-token cross-attention of a transformer block (cross_attn.cu): h += softmax_T(LN2(h) Wscore_z^T) Wout_z^T + bias,
+// one launch instead of the score / output contraction pair. h -> hout [3 * rows_z, C] (hout == h: in place); wscore [3][128][C] (LayerNorm gamma
+// folded), wout [3][C][128] per-brush operands; ln_stats: per-(32-column chunk, row) partial sums of h (gemm_tc.h)
+struct CrossOp {
+    CUtensorMap mapH, mapW1, mapW2;
+    int rows_z, C, T;
+    const float2* ln_stats;
+    const float *ln_colsum, *sbias, *obias;
+    const __half* h;
+    __half* hout;
+    int csplit;
+    float2* stats_out;
+};
+int cross_attn_setup(CrossOp* op, const __half* h, __half* hout, int rows_z, int C, int T, const __half* wscore,
+                     const __half* wout, const float2* ln_stats, const float* ln_colsum, const float* sbias, const float* obias,
+                     float2* stats_out);
+int cross_attn_launch(const CrossOp* op, cudaStream_t st);
+const char* cross_last_error();
+
 int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* out, cudaStream_t st);
 // stride-2 3x3 gather: out[(n,oy,ox)][tap*C + c] = x[n, 2*oy+ky-pad_lo, 2*ox+kx-pad_lo, c] (0 outside)
 int launch_im2col_s2(const __half* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, __half* out,

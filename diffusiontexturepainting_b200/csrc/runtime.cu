@@ -1084,7 +1084,33 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.layernorm(h, t + ".norm2", tmp.p);
     }
     const int T = cfg.enc_tokens;
-    if (e.fold_cross()) {
+    if (fl && e.fuse_cross() && heads * 16 == 128 && (C % 64) == 0) {
+        // score and output contraction as ONE kernel: the probabilities stay in shared memory (cross_attn.cu)
+        CrossOp cop;
+        const long long grp_rows = rows / 3;
+        // few row tiles (narrow levels): out of place, so that the output chunks can be spread over CTAs
+        const bool split = ((grp_rows + 127) / 128) * 3 * 2 <= 148 && C > 256;
+        Act h2 = split ? b.like(x, C) : h;
+        if (!b.ok) return Act{};
+        if (cross_attn_setup(&cop, h.p, h2.p, static_cast<int>(grp_rows), C, T, e.ln(tf).wscore, e.wout(tf), st,
+                             e.ln(tf).ws_cs, e.ln(tf).ws_b, b.F32(t + ".attn2.to_out.0.bias"), fl3 ? st : nullptr)) {
+            b.fail(std::string("cross attention setup: ") + cross_last_error());
+        } else if (b.ok) {
+            Engine* eng = &e;
+            b.plan.add(K_GEMM, [cop, eng](cudaStream_t s) -> int {
+                if (cross_attn_launch(&cop, s)) {
+                    eng->set_error(cross_last_error());
+                    return -1;
+                }
+                return 1;
+            }, "cross_attn rows=" + std::to_string(grp_rows) + " C=" + std::to_string(C) + " z=3 csplit=" +
+                   std::to_string(cop.csplit));
+        }
+        if (split) {
+            b.release(h);
+            h = h2;
+        }
+    } else if (e.fold_cross()) {
         const int HP = heads * 16;
         const long long grp_rows = rows / 3;
         Act P = b.like(x, HP);
@@ -2190,6 +2216,13 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "fold_cross") {
         opt_fold_cross_ = value;
+        unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fuse_cross") {
+        opt_fuse_cross_ = value;
         unet_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();

@@ -151,6 +151,7 @@ class Engine {
     int set_option(const char* name, int value);
     int profile_dump(const char* path);
     const char* last_error() const { return err_.c_str(); }
+    void set_error(const std::string& m) { err_ = m; }
     KernelCtx* kctx() const { return kctx_; }
     int device() const { return device_; }
     bool ok() const { return kctx_ != nullptr; }
@@ -167,6 +168,7 @@ class Engine {
     const FusedShortcut* fused_shortcut(const std::string& prefix, int cout, int cin);
     bool fold_ln() const { return opt_fold_ln_ != 0 && !ln_.empty(); }
     const LnFold& ln(int i) const { return ln_[i]; }
+    bool fuse_cross() const { return opt_fuse_cross_ != 0; }
     bool fuse_ff_out() const { return opt_fuse_ff_out_ != 0 && !ffo_.empty(); }
     const FfOut& ffo(int i) const { return ffo_[i]; }
     long long fold_ln_ff_rows() const { return opt_fold_ln_ff_rows_; }
@@ -237,6 +239,7 @@ class Engine {
     std::vector<LnFold> ln_;
     std::vector<FfOut> ffo_;
     int opt_fuse_ff_out_ = 1;
+    int opt_fuse_cross_ = 1;  // score + output contraction of the folded cross-attention as one kernel (cross_attn.cu)
     int prepare_ff_out();
     std::unordered_map<std::string, FusedShortcut> fused_sc_;
     int opt_fuse_shortcut_ = 1;

@@ -212,6 +212,27 @@ def test_full_unet(full):
     check_unet(full, 256, name="sd15")
 
 
+def test_full_fused_cross_attention_matches_the_two_kernel_path(full):
+    """cross_attn_kernel (scores + softmax + output in one launch; needs 8 heads, so only the full model uses it) against
+    the two-contraction path on the same UNet evaluation: levels with 4096 / 1024 / 256 / 64 rows per sample group (R = 512)
+    and ragged tiles (R = 64: 64 / 16 / 4 / 1 rows)."""
+    h_sizes = (512, 64)
+    for R in h_sizes:
+        h = R // 8
+        sample = torch.randn(3, 9, h, h, generator=gen(17)).to(DEV)
+        emb = torch.randn(14, full.cfg.unet.cross_dim, generator=gen(18)).to(DEV)
+        full.engine.set_condition(emb, emb * 0.3)
+        full.engine.set_schedule([501.0], [0.5], [0.6], 2.0, 1.0, 1)
+        outs = []
+        for on in (1, 0):
+            full.engine.set_option("fuse_cross", on)
+            outs.append(full.engine.unet_forward(sample, 0).clone())
+        full.engine.set_option("fuse_cross", 1)
+        e = rel_l2(outs[0], outs[1])
+        log(f"sd15.cross_fused_vs_split.R{R}", rel_l2=e)
+        assert e < 2e-3
+
+
 def test_full_vae(full):
     check_vae(full, 128, B=1, name="sd15")
 
@@ -297,7 +318,10 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     eng.set_option("fuse_ff_out", 0)   # ff.net.2 and proj_out as two contractions
     outs["ff_out_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
     eng.set_option("fuse_ff_out", 1)
-    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate"):
+    eng.set_option("fuse_cross", 0)   # cross-attention as two contractions (scores with softmax epilogue, output)
+    outs["cross_two_kernels"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("fuse_cross", 1)
+    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate", "cross_two_kernels"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
