@@ -167,8 +167,9 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
 /* counters: "launches" (kernels launched by this engine so far), "stamps", "arena_peak", "arena_bytes", "graph_launches",
  * "unet_plan_ops", "device", "stage_us_<k>" / "stage_n_<k>" (k = 0..5: canvas_preprocess, vae_encoder, unet, latent_step,
  * vae, composite; device time and count accumulated since dtp_set_option("stage_timers", 1)).
- * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fold_ln" (LayerNorm folded into the consuming
- * contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside conv2), "flash", "profile" (per-op events),
+ * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fuse_cross" (image-token cross-attention as one
+ * launch), "fold_ln" (LayerNorm folded into the consuming contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside
+ * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "flash", "profile" (per-op events),
  * "stage_timers", "nvtx" (NVTX ranges per stage), "arena_mib" (grow the activation arena to at least this size). */
 long long dtp_get_counter(dtp_handle* h, const char* name);
 int dtp_set_option(dtp_handle* h, const char* name, int value);
