@@ -334,6 +334,166 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Register-resident GroupNorm, one CTA per (group, sample): groups are independent, so a CTA that owns a whole group needs
+// no cross-CTA barrier at all - load once (every load of a thread in flight together), two in-CTA reductions (mean, then
+// centred variance: the two-pass form), normalise out of registers. V halfs per vector (cpg % V == 0), at most EPT vectors per
+// thread; the block size is a multiple of the vectors per pixel, so a thread's channel slot (and its gamma / beta, fetched
+// before the dependency wait) is fixed.
+template <int V>
+struct HalfVec;
+template <>
+struct HalfVec<8> {
+    using T = uint4;
+};
+template <>
+struct HalfVec<4> {
+    using T = uint2;
+};
+template <>
+struct HalfVec<2> {
+    using T = uint32_t;
+};
+
+__device__ __forceinline__ float gn_block_sum(float v, float* red, int warp, int lane) {
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < static_cast<int>(blockDim.x >> 5)) ? red[lane] : 0.0f;
+    t = warp_sum(t);  // every warp folds the same NW values in the same order
+    __syncthreads();
+    return t;
+}
+
+template <int V, int EPT>
+__global__ void __launch_bounds__(960)
+    gn_group2_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1, int HW, int groups,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                     __half* __restrict__ out) {
+    using VT = typename HalfVec<V>::T;
+    __shared__ float red[32];
+    const int C = C0 + C1;
+    const int cpg = C / groups;
+    const int vp = cpg / V;  // vectors per pixel of this group
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int j = threadIdx.x % vp, prow = threadIdx.x / vp, rows_per_iter = blockDim.x / vp;
+    const int c = g * cpg + j * V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float ga[V], be[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        ga[e] = __ldg(gamma + c + e);
+        be[e] = __ldg(beta + c + e);
+    }
+    const __half* src;
+    int ldc;
+    if (c < C0) {
+        src = x0 + static_cast<long long>(n) * HW * C0 + c;
+        ldc = C0;
+    } else {
+        src = x1 + static_cast<long long>(n) * HW * C1 + (c - C0);
+        ldc = C1;
+    }
+    pdl_wait();
+    VT v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int p = prow + k * rows_per_iter;
+        if (p < HW) v[k] = *reinterpret_cast<const VT*>(src + static_cast<long long>(p) * ldc);
+    }
+    pdl_launch_dependents();
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        if (prow + k * rows_per_iter < HW) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) {
+                const float2 f = __half22float2(h[e]);
+                s += f.x + f.y;
+            }
+        }
+    }
+    const float inv_count = 1.0f / (static_cast<float>(HW) * static_cast<float>(cpg));
+    const float mean = gn_block_sum(s, red, warp, lane) * inv_count;
+    float ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        if (prow + k * rows_per_iter < HW) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) {
+                const float2 f = __half22float2(h[e]);
+                const float a = f.x - mean, b = f.y - mean;
+                ss = fmaf(a, a, ss);
+                ss = fmaf(b, b, ss);
+            }
+        }
+    }
+    const float var = gn_block_sum(ss, red, warp, lane) * inv_count + eps;
+    float rstd = rsqrtf(var);
+    rstd = rstd * (1.5f - 0.5f * var * rstd * rstd);
+    float sc[V], sh[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        sc[e] = rstd * ga[e];
+        sh[e] = be[e] - mean * sc[e];
+    }
+    __half* dst = out + static_cast<long long>(n) * HW * C + c;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int p = prow + k * rows_per_iter;
+        if (p < HW) {
+            VT o;
+            const __half2* h = reinterpret_cast<const __half2*>(&v[k]);
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < V / 2; ++e) {
+                const float2 f = __half22float2(h[e]);
+                float y0 = fmaf(f.x, sc[2 * e], sh[2 * e]), y1 = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+                if (silu) {
+                    y0 = silu_f(y0);
+                    y1 = silu_f(y1);
+                }
+                oh[e] = __floats2half2_rn(y0, y1);
+            }
+            *reinterpret_cast<VT*>(dst + static_cast<long long>(p) * C) = o;
+        }
+    }
+}
+
+template <int V>
+static int launch_gn_group2(int ept, dim3 grid, int threads, cudaStream_t st, const __half* x0, int C0, const __half* x1, int C1,
+                            int HW, int groups, const float* gamma, const float* beta, float eps, int silu, __half* out) {
+#define GN_G2(E) launch_k(gn_group2_kernel<V, E>, grid, dim3(threads), 0, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out)
+    // instantiations hold at most 22 data registers per thread (ept * V / 2)
+    if (ept <= 2)
+        GN_G2(2);
+    else if (ept <= 5)
+        GN_G2(5);
+    else if constexpr (V <= 4) {
+        if (ept <= 11)
+            GN_G2(11);
+        else if constexpr (V == 2) {
+            if (ept <= 16)
+                GN_G2(16);
+            else
+                GN_G2(22);
+        }
+    }
+#undef GN_G2
+    return check_launch("gn_group2");
+}
+
+// 0: never, 1: by the measured rule, 2: whenever the shape allows (benchmarking)
+static int gn_group2_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DTP_GN_GROUP");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 // Single-launch GroupNorm for tensors that fit the SMs' shared memory (every UNet GroupNorm at B <= 4): the CTAs of a sample
 // keep their row slab in smem, publish per-group partial sums, meet at a per-sample barrier (all CTAs are co-resident:
 // grid <= #SMs, one CTA per SM), fold the partials in a fixed order and normalise straight out of smem. The tensor is
@@ -571,6 +731,31 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
         return -1;
     }
     const int cpg = C / groups;
+    if (gn_group2_mode() != 0) {
+        // vector width: the widest that divides the group and keeps every vector inside one source
+        const int V = (cpg % 8 == 0) ? 8 : (cpg % 4 == 0) ? 4 : (cpg % 2 == 0) ? 2 : 0;
+        const int vp = V ? cpg / V : 0;
+        if (V && vp <= 30 && (C0 % V) == 0) {
+            int lcm = vp;  // block size: a multiple of the vectors per pixel and of the warp size
+            while (lcm % 32) lcm += vp;
+            const long long total = static_cast<long long>(HW) * vp;
+            int threads = static_cast<int>(((total + lcm - 1) / lcm) * lcm);
+            if (threads > 960) threads = (960 / lcm) * lcm;
+            const int ept = threads > 0 ? static_cast<int>((HW + threads / vp - 1) / (threads / vp)) : 1 << 30;
+            const bool fits = threads > 0 && ept * V <= 44;  // data registers per thread (64-register cap at 960 threads)
+            // measured (profiles/gn_bench.py, B200): the barrier-free kernel wins while a group is small enough that one
+            // CTA streams it faster than the multi-CTA kernel's publish / barrier / fold chain (~3.5 us) costs
+            const int sms = gn_sm_count();
+            const long long waves = (static_cast<long long>(Nimg) * groups + sms - 1) / sms;
+            const bool rule = static_cast<long long>(HW) * cpg * waves <= 24576;
+            if (fits && (gn_group2_mode() == 2 || rule)) {
+                const dim3 grid(groups, Nimg);
+                if (V == 8) return launch_gn_group2<8>(ept, grid, threads, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+                if (V == 4) return launch_gn_group2<4>(ept, grid, threads, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+                return launch_gn_group2<2>(ept, grid, threads, st, x0, C0, x1, C1, HW, groups, gamma, beta, eps, silu, out);
+            }
+        }
+    }
     if (gn_fused_enabled() && CV <= 512 && Nimg <= gn_sm_count() && Nimg <= kGnSamples) {
         // block = CV * rows_per_iter threads, a multiple of 32 (the group reductions use full-warp shuffles)
         int gcd = CV, t32 = 32;

@@ -18,7 +18,7 @@ dev = "cuda"
 SHAPES = [  # (Nimg, HW, C0, C1)
     (3, 4096, 320, 0), (3, 4096, 320, 320), (3, 4096, 640, 320), (3, 1024, 640, 0), (3, 1024, 640, 640),
     (3, 1024, 1280, 640), (3, 1024, 320, 0), (3, 256, 1280, 0), (3, 256, 1280, 1280), (3, 256, 640, 0),
-    (3, 64, 1280, 0), (3, 64, 1280, 1280), (12, 1024, 320, 0), (12, 1024, 640, 320), (12, 256, 640, 0),
+    (3, 64, 1280, 0), (3, 64, 1280, 1280), (3, 1024, 640, 320), (3, 256, 1280, 640), (12, 1024, 320, 0), (12, 1024, 640, 320), (12, 256, 640, 0),
     (12, 64, 1280, 1280), (2, 4096, 512, 0), (1, 16384, 512, 0),
 ]
 
@@ -66,7 +66,7 @@ def run(n, hw, c0, c1):
 
 
 if __name__ == "__main__":
-    print("DTP_GN_FUSED=%s" % os.environ.get("DTP_GN_FUSED", "1"))
+    print("DTP_GN_FUSED=%s DTP_GN_GROUP=%s" % (os.environ.get("DTP_GN_FUSED", "1"), os.environ.get("DTP_GN_GROUP", "1")))
     for shp in SHAPES:
         us, err, same = run(*shp)
         n, hw, c0, c1 = shp
