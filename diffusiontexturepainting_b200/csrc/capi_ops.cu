@@ -111,6 +111,22 @@ int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, con
     return finish(op, r, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
 }
 
+int dtp_op_upconv2x(const void* A, int C, int Nimg, int H, int W, const void* Wt, int Cout, const float* bias, void* wstack,
+                    void* out, int BN, void* stream) {
+    if (Wt != nullptr && launch_upconv_fold_weights((const __half*)Wt, Cout, C, (__half*)wstack, (cudaStream_t)stream)) return -1;
+    GemmOp op;
+    if (BN <= 0) {
+        int sp = 1;
+        GemmOp probe;
+        int r0 = gemm_setup_upconv2x(&probe, (const __half*)A, C, Nimg, H, W, (const __half*)wstack, Cout, 128);
+        if (r0) return finish(probe, r0, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+        gemm_pick_config(4 * probe.grid_m, Cout, probe.p.num_kb, (probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0,
+                         &BN, &sp);
+    }
+    int r = gemm_setup_upconv2x(&op, (const __half*)A, C, Nimg, H, W, (const __half*)wstack, Cout, BN);
+    return finish(op, r, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+}
+
 int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
                long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
                long long out_zs2, float alpha, int flags, int BN, void* stream) {

@@ -342,7 +342,9 @@ __device__ __forceinline__ int tile_row(const GemmParams& p, const TileCoord& c,
         const int hh = (r / p.bw) % p.bh;
         const int nn = r / (p.bw * p.bh);
         const int img = c.img0 + nn;
-        return (img < p.Nimg) ? (img * p.H + c.y0 + hh) * p.W + c.x0 + w : -1;
+        if (img >= p.Nimg) return -1;
+        if (p.up2) return (img * 2 * p.H + 2 * (c.y0 + hh) + (c.z1 >> 1)) * 2 * p.W + 2 * (c.x0 + w) + (c.z1 & 1);
+        return (img * p.H + c.y0 + hh) * p.W + c.x0 + w;
     }
     const int m = c.m_tile * 128 + r;
     return (m < p.M) ? m : -1;
@@ -446,7 +448,8 @@ __global__ void __launch_bounds__(320, OCC)
             // weight-streaming layers behind the previous kernel's tail. Activations (A) are only touched after the wait.
             int pre = 0;
             if (!p.b_batched && !b_mn && tile0 < total_tiles) {
-                const TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
+                TileCoord c0 = decode_tile<BN, CL>(p, tile0, rank);
+                if (p.up2) c0.n0 += c0.z1 * p.N;  // weight rows of the parity class
                 const bool ragged0 = p.n_last > 0 && c0.n_tile == p.grid_n - 1;
                 const CUtensorMap* mB0 = ragged0 ? &mapBL : &mapB;
                 const uint32_t b0_bytes = ragged0 ? static_cast<uint32_t>(p.n_last / CL) * 128u : b_bytes;
@@ -479,7 +482,8 @@ __global__ void __launch_bounds__(320, OCC)
                 const bool ragged = p.n_last > 0 && c.n_tile == p.grid_n - 1;
                 const CUtensorMap* mB = ragged ? &mapBL : &mapB;
                 const uint32_t tile_b_bytes = ragged ? static_cast<uint32_t>(p.n_last / CL) * 128u : b_bytes;
-                const int brow = c.n0 + rank * ((ragged ? p.n_last : BN) / CL);
+                const int wrow0 = c.n0 + (p.up2 ? c.z1 * p.N : 0);  // first weight row of the tile
+                const int brow = wrow0 + rank * ((ragged ? p.n_last : BN) / CL);
                 for (int kb = c.kb_begin; kb < c.kb_end; ++kb) {
                     const bool prefetched = (wave == 0) && (kb - c.kb_begin) < pre;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -491,7 +495,11 @@ __global__ void __launch_bounds__(320, OCC)
                     if (p.mode == 1) {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
-                        const int ky = tap / 3, kx = tap - ky * 3;
+                        int ky = tap / 3, kx = tap - ky * 3;
+                        if (p.up2) {  // 2x2 taps of the parity class, offsets (s - 1 + parity)
+                            ky = (tap >> 1) + (c.z1 >> 1);
+                            kx = (tap & 1) + (c.z1 & 1);
+                        }
                         if (tap >= 9) {
                             // fused 1x1 shortcut: unshifted boxes of the shortcut's own sources
                             const int sb = kb - 9 * p.cblocks;
@@ -516,11 +524,11 @@ __global__ void __launch_bounds__(320, OCC)
 #pragma unroll
                         for (int j = 0; j < NSUB; ++j)
                             tma_load_4d_pair(sb + j * (BNS / CL) * 128, mB, &full_bar[stage], kb * 64,
-                                             NSUB == 1 ? brow : c.n0 + j * BNS + rank * (BNS / CL), 0, 0);
+                                             NSUB == 1 ? brow : wrow0 + j * BNS + rank * (BNS / CL), 0, 0);
                     } else if (w_blocked) {
                         tma_load_4d(sb, &mapB, &full_bar[stage], 0, 0, kb, c.n0 >> 6);
                     } else if (!b_mn) {
-                        tma_load_4d(sb, mB, &full_bar[stage], kb * 64, c.n0, bz1, bz2);
+                        tma_load_4d(sb, mB, &full_bar[stage], kb * 64, wrow0, bz1, bz2);
                     } else {
 #pragma unroll
                         for (int j = 0; j < B_CHUNKS; ++j)
@@ -1251,6 +1259,86 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
         rm = map_rows(&op->mapB, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
     if (rm) return rm;
     return setup_ragged(op, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
+}
+
+int gemm_setup_upconv2x(GemmOp* op, const __half* A, int C, int Nimg, int H, int W, const __half* Wstack, int Cout, int BN) {
+    params_defaults(op->p);
+    GemmParams& p = op->p;
+    const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
+    BN = fix_bn(BN & ~GEMM_BN_PAIR);
+    if (BN == 320 && !(want_pair && Cout % 320 == 0)) BN = 256;
+    if ((C % 64) != 0) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "upconv2x needs C %% 64 == 0 (C=%d)", C);
+        return -11;
+    }
+    if ((Cout % BN) != 0 && (Cout % 16) != 0) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "upconv2x needs Cout %% 16 == 0 (Cout=%d)", Cout);
+        return -11;
+    }
+    const int KT = 4 * C;
+    p.M = Nimg * H * W;  // rows per parity class
+    p.N = Cout;
+    p.mode = 1;
+    p.up2 = 1;
+    p.nz1 = 4;
+    p.H = H;
+    p.W = W;
+    p.Nimg = Nimg;
+    p.bw = largest_divisor_le(W, 128);
+    p.bh = largest_divisor_le(H, 128 / p.bw);
+    p.bn = (p.bh == H) ? (128 / (p.bw * p.bh)) : 1;
+    if (p.bn > Nimg) p.bn = Nimg;
+    if (p.bn < 1) p.bn = 1;
+    p.tiles_x = W / p.bw;
+    p.tiles_y = H / p.bh;
+    p.rows_valid = p.bw * p.bh * p.bn;
+    p.cblocks0 = C / 64;
+    p.cblocks = C / 64;
+    p.num_kb = 4 * p.cblocks;
+    p.splits = 1;
+    bind_ctx(op);
+    p.ldc = Cout;
+    op->BN = BN;
+    op->grid_m = p.tiles_x * p.tiles_y * ((Nimg + p.bn - 1) / p.bn);
+    if (BN == 320 && op->grid_m < 2) {
+        BN = 256;
+        op->BN = 256;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+        uint64_t st[3] = {(uint64_t)C * 2, (uint64_t)C * 2 * W, (uint64_t)C * 2 * W * H};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+        int r = make_map_4d(&op->mapA0, A, dims, st, box);
+        if (r) return r;
+    }
+    op->mapA1 = op->mapA0;
+    op->mapA2 = op->mapA0;
+    op->mapA3 = op->mapA0;
+    op->cluster = 1;
+    const uint64_t wrows = 4ull * Cout;
+    if (want_pair && op->grid_m >= 2 && BN >= 32) {
+        if (map_rows(&op->mapBh, Wstack, (uint64_t)KT, wrows, (uint64_t)KT, BN > 256 ? BN / 4 : BN / 2)) return -13;
+        op->cluster = 2;
+    }
+    int rm = 0;
+    if (BN > 256)
+        op->mapB = op->mapBh;
+    else
+        rm = map_rows(&op->mapB, Wstack, (uint64_t)KT, wrows, (uint64_t)KT, BN);
+    if (rm) return rm;
+    // ragged last n-tile: its box may run into the next class's rows; those columns are >= N and never stored
+    p.n_last = 0;
+    op->mapBL = (op->cluster == 2) ? op->mapBh : op->mapB;
+    const int rows_last = Cout % BN;
+    if (rows_last != 0) {
+        const int n_last = (rows_last + 15) & ~15;
+        if (n_last < BN) {
+            if (map_rows(&op->mapBL, Wstack, (uint64_t)KT, wrows, (uint64_t)KT, static_cast<uint32_t>(op->cluster == 2 ? n_last / 2 : n_last)))
+                return -14;
+            p.n_last = n_last;
+        }
+    }
+    return 0;
 }
 
 int gemm_setup_batched(GemmOp* op, const __half* A, int lda, long long a_zs1, long long a_zs2, const __half* B, int ldb,

@@ -89,6 +89,10 @@ struct GemmParams {
     float2* stats_out;        // [N / 32][stats_rows]; needs N % 32 == 0 and a plain fp16 row-major output
     int stats_rows;
     long long bias_zs1;       // bias / ln_colsum offset (elements) per batch coordinate z1 (folded cross-attention scores)
+    // ---- nearest-2x upsample folded into the 3x3 convolution that follows it (gemm_setup_upconv2x): z1 = output parity class
+    // (py, px); the class's four 2x2 taps read the HALF-resolution input at (y + sy - 1 + py, x + sx - 1 + px); weight rows of
+    // class z1 start at z1 * N; output pixel = (2y + py, 2x + px) of the (2H, 2W) image
+    int up2;
 };
 
 struct GemmOp {
@@ -110,6 +114,10 @@ int make_map_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const 
 
 // Linear problem: A0 [M, K0] (row stride lda0) and optional A1 [M, K1] (K0 % 64 == 0 when A1 is used);
 // Wt [N, K0+K1] row-major (row stride ldw). Strides in elements, multiples of 8.
+// conv3x3(nearest_upsample_2x(x)) as four parity-class 2x2 convolutions over x itself (4/9 of the multiply-adds, no upsampled
+// tensor): A [Nimg, H, W, C] fp16 NHWC (C % 64 == 0), Wstack [4 * Cout, 4 * C] from launch_upconv_fold_weights, output
+// [Nimg, 2H, 2W, ldc]. One launch, batch coordinate z1 = parity class.
+int gemm_setup_upconv2x(GemmOp* op, const __half* A, int C, int Nimg, int H, int W, const __half* Wstack, int Cout, int BN);
 int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
                       const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked = 0);
 // 3x3/s1/p1 conv over NHWC activations: sources (Nimg,H,W,C0) and optional (Nimg,H,W,C1), C0,C1 % 64 == 0;

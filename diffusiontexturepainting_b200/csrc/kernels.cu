@@ -830,6 +830,36 @@ int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nim
     return check_launch("gn_apply");
 }
 
+// Weights of conv3x3(nearest_upsample_2x(x)) as four parity-class 2x2 convolutions over x (gemm_setup_upconv2x):
+//   Wst[(py*2+px) * Cout + o][(sy*2+sx) * C + c] = sum over the 3x3 taps (ky, kx) that land on input offset
+//   (sy - 1 + py, sx - 1 + px), i.e. ky in S(py, sy), kx in S(px, sx) with S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1},
+//   S(1,1) = {2}; summed in fp32, rounded to fp16 once.
+__global__ void __launch_bounds__(256) upconv_fold_weights_kernel(const __half* __restrict__ W, int Cout, int C,
+                                                                  __half* __restrict__ Wst) {
+    const long long total = 16LL * Cout * C;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    const int s = static_cast<int>(r & 3);
+    r >>= 2;
+    const int o = static_cast<int>(r % Cout);
+    const int cls = static_cast<int>(r / Cout);
+    const int py = cls >> 1, px = cls & 1, sy = s >> 1, sx = s & 1;
+    const int ky0 = (py == 0) ? (sy == 0 ? 0 : 1) : (sy == 0 ? 0 : 2), ky1 = (py == 0) ? (sy == 0 ? 0 : 2) : (sy == 0 ? 1 : 2);
+    const int kx0 = (px == 0) ? (sx == 0 ? 0 : 1) : (sx == 0 ? 0 : 2), kx1 = (px == 0) ? (sx == 0 ? 0 : 2) : (sx == 0 ? 1 : 2);
+    const __half* w = W + static_cast<long long>(o) * 9 * C + c;
+    float acc = 0.0f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+        for (int kx = kx0; kx <= kx1; ++kx) acc += __half2float(w[(ky * 3 + kx) * C]);
+    Wst[(static_cast<long long>(cls) * Cout + o) * 4 * C + s * C + c] = __float2half_rn(acc);
+}
+int launch_upconv_fold_weights(const __half* W, int Cout, int C, __half* Wst, cudaStream_t st) {
+    const long long total = 16LL * Cout * C;
+    upconv_fold_weights_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(W, Cout, C, Wst);
+    return check_launch("upconv_fold_weights");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 2048), two-pass variance
 // ------------------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@ void kernels_set_debug(long long* dbg);
 // stats_ws: float[Nimg * chunks * groups * 2 + Nimg * groups * 2]
 int gn_num_chunks(int HW, int C);
 size_t gn_ws_floats(int Nimg, int HW, int C, int groups);
+// folds conv3x3(nearest_upsample_2x(.)) weights [Cout, 9*C] into the stacked parity-class weights [4*Cout, 4*C] (gemm_tc.h)
+int launch_upconv_fold_weights(const __half* W, int Cout, int C, __half* Wst, cudaStream_t st);
 int launch_groupnorm(const __half* x0, int C0, const __half* x1, int C1, int Nimg, int HW, int groups,
                      const float* gamma, const float* beta, float eps, int silu, __half* out, float* stats_ws,
                      cudaStream_t st, int* launches = nullptr);  // *launches: kernels enqueued (1 or 2)

@@ -96,11 +96,21 @@ void Profiler::reset() {
 // Measurement aid (dtp_set_option("debug_skip_kinds", mask)): ops whose kind bit is set are not launched, so the in-graph
 // cost of a kernel family is the difference of two stamp times. Results are garbage while it is non-zero.
 static int g_debug_skip_kinds = 0;
+// same, per op label: dtp_set_option("debug_skip_label", h) leaves out the ops whose label hashes to h (31-bit FNV-1a of the
+// label text as dtp_profile_dump prints it; profiles/ablate_labels.py)
+static int g_debug_skip_label = 0;
+static int label_hash(const std::string& s) {
+    unsigned h = 2166136261u;
+    for (unsigned char c : s) h = (h ^ c) * 16777619u;
+    h &= 0x7fffffffu;
+    return h ? static_cast<int>(h) : 1;
+}
 
 int Plan::run(cudaStream_t st, long long* launch_counter, Profiler* prof) const {
     const bool p = prof && prof->on;
     for (size_t i = 0; i < ops.size(); ++i) {
         if (g_debug_skip_kinds && i < kinds.size() && ((g_debug_skip_kinds >> kinds[i]) & 1)) continue;
+        if (g_debug_skip_label && i < labels.size() && label_hash(labels[i]) == g_debug_skip_label) continue;
         cudaEvent_t a = nullptr, b = nullptr;
         if (p) {
             a = prof->get();
@@ -516,6 +526,48 @@ struct Builder {
         release_raw(S);
     }
 
+    // Upsample2D (nearest 2x, then conv 3x3): one contraction over the half-resolution input when the fold is on
+    Act upsample_conv(const Act& x, const std::string& p) {
+        if (!ok) return Act{};
+        int cout = 0, kk = 0;
+        const __half* W = W16(p + ".weight", &cout, &kk);
+        if (!ok) return Act{};
+        const long long rows_out = 4LL * x.N * x.H * x.W;
+        if (!e.opt_fold_upsample_ || (x.C % 64) != 0 || kk != 9 * x.C || rows_out < e.opt_fold_upsample_rows_) {
+            Act up = upsample2x(x);
+            Act y = conv3x3(up, Act{}, p, nullptr, nullptr);
+            release(up);
+            return y;
+        }
+        const __half* Wst = e.upconv_weights(prefix + p, W, cout, x.C);
+        const float* bias = F32(p + ".bias");
+        if (!Wst || !ok) {
+            ok = false;
+            return Act{};
+        }
+        Act out = alloc(x.N, 2 * x.H, 2 * x.W, cout);
+        if (!ok) return out;
+        GemmOp probe, op;
+        if (gemm_setup_upconv2x(&probe, x.p, x.C, x.N, x.H, x.W, Wst, cout, 128)) {
+            fail(std::string("upconv setup: ") + gemm_last_error());
+            return out;
+        }
+        int BN, splits;
+        gemm_pick_config(4 * probe.grid_m, cout, probe.p.num_kb,
+                         (probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0, &BN, &splits);
+        // measured (profiles/upconv_bench.py): 256-wide tiles everywhere, as CTA pairs once there are several waves of them
+        BN = (4 * probe.grid_m >= 512 && cout % 256 == 0) ? (256 | GEMM_BN_PAIR) : 256;
+        if (gemm_setup_upconv2x(&op, x.p, x.C, x.N, x.H, x.W, Wst, cout, BN)) {
+            fail(std::string("upconv setup: ") + gemm_last_error());
+            return out;
+        }
+        op.p.bias = bias;
+        op.p.out = out.p;
+        op.p.ldc = cout;
+        push_gemm(op, "upconv2x");
+        return out;
+    }
+
     Act upsample2x(const Act& x) {
         if (!ok) return Act{};
         Act out = alloc(x.N, 2 * x.H, 2 * x.W, x.C);
@@ -734,6 +786,19 @@ const Engine::FusedShortcut* Engine::fused_shortcut(const std::string& prefix, i
     return &fused_sc_.emplace(prefix, f).first->second;
 }
 
+const __half* Engine::upconv_weights(const std::string& key, const __half* W, int cout, int cin) {
+    auto it = upconv_w_.find(key);
+    if (it != upconv_w_.end()) return it->second;
+    __half* wst = static_cast<__half*>(persistent(16ull * cout * cin * sizeof(__half), false));
+    if (!wst) return nullptr;
+    if (launch_upconv_fold_weights(W, cout, cin, wst, nullptr) || cudaDeviceSynchronize() != cudaSuccess) {
+        fail(std::string("upsample-conv weight fold failed: ") + kernels_last_error());
+        return nullptr;
+    }
+    upconv_w_.emplace(key, wst);
+    return wst;
+}
+
 int Engine::check_device_error() {
     const int v = kctx_take_error(kctx_);
     if (v == 0) return 0;
@@ -920,6 +985,7 @@ int Engine::finalize_weights() {
     temb_dirty_ = true;
     cond_set_ = false;
     fused_sc_.clear();
+    upconv_w_.clear();
     if (prepare_ln_fold()) return -1;
     if (prepare_ff_out()) return -1;
     finalized_ = true;
@@ -1294,10 +1360,9 @@ int Engine::build_unet_plan(int B, int R) {
             x = y;
         }
         if (i != 3 && b.ok) {
-            Act up = b.upsample2x(x);
+            Act up = b.upsample_conv(x, "up_blocks." + std::to_string(i) + ".upsamplers.0.conv");
             b.release(x);
-            x = b.conv3x3(up, Act{}, "up_blocks." + std::to_string(i) + ".upsamplers.0.conv", nullptr, nullptr);
-            b.release(up);
+            x = up;
         }
     }
     if (b.ok) {
@@ -1453,10 +1518,9 @@ int Engine::build_vae_dec_plan(int B, int R) {
             x = y;
         }
         if (i != 3 && b.ok) {
-            Act up = b.upsample2x(x);
+            Act up = b.upsample_conv(x, "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv");
             b.release(x);
-            x = b.conv3x3(up, Act{}, "decoder.up_blocks." + std::to_string(i) + ".upsamplers.0.conv", nullptr, nullptr);
-            b.release(up);
+            x = up;
         }
     }
     if (b.ok) {
@@ -2235,6 +2299,14 @@ int Engine::set_option(const char* name, int value) {
         g_stamp_.key.clear();
         return 0;
     }
+    if (n == "fold_upsample" || n == "fold_upsample_rows") {
+        (n == "fold_upsample" ? opt_fold_upsample_ : opt_fold_upsample_rows_) = value;
+        unet_plan_.clear();
+        vae_dec_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
     if (n == "fuse_shortcut") {
         opt_fuse_shortcut_ = value;
         unet_plan_.clear();
@@ -2267,6 +2339,12 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "debug_skip_kinds") {
         g_debug_skip_kinds = value;
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "debug_skip_label") {
+        g_debug_skip_label = value;
         g_infer_.key.clear();
         g_stamp_.key.clear();
         return 0;

@@ -166,6 +166,9 @@ class Engine {
         float* bias = nullptr;
     };
     const FusedShortcut* fused_shortcut(const std::string& prefix, int cout, int cin);
+    // Upsample2D conv weights folded into the four parity-class 2x2 convolutions ([4*cout, 4*cin], kernels.h
+    // launch_upconv_fold_weights): built on first use, cached per conv prefix
+    const __half* upconv_weights(const std::string& key, const __half* W, int cout, int cin);
     bool fold_ln() const { return opt_fold_ln_ != 0 && !ln_.empty(); }
     const LnFold& ln(int i) const { return ln_[i]; }
     bool fuse_cross() const { return opt_fuse_cross_ != 0; }
@@ -243,6 +246,9 @@ class Engine {
     int prepare_ff_out();
     std::unordered_map<std::string, FusedShortcut> fused_sc_;
     int opt_fuse_shortcut_ = 1;
+    std::unordered_map<std::string, __half*> upconv_w_;
+    int opt_fold_upsample_ = 1;          // nearest-2x upsample folded into its convolution (gemm_setup_upconv2x)
+    int opt_fold_upsample_rows_ = 3072;  // ... for outputs of at least this many pixels (below, the 16/9 larger folded weights cost more than the multiply-adds save)
     int opt_fold_ln_ = 1;
     int opt_fold_ln_ff_rows_ = 1024;  // norm3 -> FF1 folding only for activations of at most this many rows
     int prepare_ln_fold();

@@ -71,6 +71,13 @@ int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int
  * rows appended along K), bias = conv2.bias + conv_shortcut.bias (diffusers ResnetBlock2D.forward: output = shortcut(x) + h) */
 int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, const void* S1, int CS1, int Nimg, int H, int W,
                             const void* Wt, int Cout, const float* bias, void* out, int BN, int splits, void* stream);
+/* Upsample2D (diffusers: F.interpolate(scale_factor=2, mode="nearest") then conv 3x3 pad 1; the reference's graph folds the
+ * resize, models.py:128-186) as ONE contraction over the half-resolution input: four output-parity classes, each a 2x2
+ * convolution with pre-summed taps (4/9 of the multiply-adds, no upsampled tensor). A (Nimg,H,W,C) NHWC f16, Wt [Cout, 9*C]
+ * (the conv's packed weights; NULL = wstack already holds the folded weights of an earlier call), wstack: the folded weights
+ * [4*Cout, 4*C] f16, out (Nimg,2H,2W,Cout) f16. */
+int dtp_op_upconv2x(const void* A, int C, int Nimg, int H, int W, const void* Wt, int Cout, const float* bias, void* wstack,
+                    void* out, int BN, void* stream);
 /* batched D_z = alpha * A_z * B_z^T over z = (z1 < nz1, z2 < nz2); b_mn: B_z given as [K,N] row-major */
 int dtp_op_bmm(const void* A, int lda, long long a_zs1, long long a_zs2, const void* B, int ldb, long long b_zs1,
                long long b_zs2, int b_mn, int M, int N, int K, int nz1, int nz2, void* out, int ldc, long long out_zs1,
@@ -169,7 +176,8 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
  * vae, composite; device time and count accumulated since dtp_set_option("stage_timers", 1)).
  * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fuse_cross" (image-token cross-attention as one
  * launch), "fold_ln" (LayerNorm folded into the consuming contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside
- * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "flash", "profile" (per-op events),
+ * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "fold_upsample" (nearest-2x upsample
+ * folded into its 3x3 convolution; "fold_upsample_rows": smallest output pixel count it applies to), "flash", "profile" (per-op events),
  * "stage_timers", "nvtx" (NVTX ranges per stage), "arena_mib" (grow the activation arena to at least this size). */
 long long dtp_get_counter(dtp_handle* h, const char* name);
 int dtp_set_option(dtp_handle* h, const char* name, int value);

@@ -27,6 +27,8 @@ ap.add_argument("--profiler-range", action="store_true",
                 help="cudaProfilerStart/Stop around the measured stamps (ncu --profile-from-start off)")
 ap.add_argument("--ablate", action="store_true",
                 help="graph-mode stamp time with each kernel family skipped in turn (in-situ cost = difference)")
+ap.add_argument("--ablate-labels", type=int, default=0, metavar="N",
+                help="in-graph cost of the N most expensive op labels (stamp time with that label's launches left out)")
 a = ap.parse_args()
 R, S, B = a.resolution, a.denoise_steps, a.batch
 model = TRTConditionalInpainter(R, device=0, model_config=W.sd15_config(), max_batch_size=B)
@@ -64,6 +66,54 @@ if a.ablate:
         t = timed()
         print("  without %-12s %.2f ms  -> in-situ cost %.2f ms" % (name, t, base - t), flush=True)
     eng.set_option("debug_skip_kinds", 0)
+    sys.exit(0)
+if a.ablate_labels:
+    import csv
+
+    def fnv(text):
+        h = 2166136261
+        for ch in text.encode():
+            h = ((h ^ ch) * 16777619) & 0xffffffff
+        return (h & 0x7fffffff) or 1
+
+    def timed(n=3):
+        for _ in range(2):
+            eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    eng.set_option("graph", 0)
+    eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+    eng.set_option("profile", 1)
+    eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
+    torch.cuda.synchronize()
+    path = os.path.join(ROOT, "gpurun_out", f"{a.tag}_ops.csv")
+    eng.profile_dump(path)
+    eng.set_option("profile", 0)
+    eng.set_option("graph", 1)
+    rows = list(csv.DictReader(open(path)))[:a.ablate_labels]
+    base = timed(5)
+    lines = ["label,calls,eager_avg_us,in_graph_avg_us,in_graph_total_ms", "# graph-mode stamp %.3f ms" % base]
+    total = 0.0
+    for r in rows:
+        eng.set_option("debug_skip_label", fnv(r["op"]))
+        t = timed()
+        calls = int(r["calls"])
+        cost = base - t
+        total += cost
+        lines.append("%s,%d,%.2f,%.2f,%.3f" % (r["op"], calls, float(r["avg_us"]), cost * 1e3 / calls, cost))
+        print(lines[-1], flush=True)
+    eng.set_option("debug_skip_label", 0)
+    lines.append("# sum of the listed in-graph costs %.2f ms of %.2f ms" % (total, base))
+    print(lines[-1])
+    open(os.path.join(ROOT, "gpurun_out", f"{a.tag}_label_costs.csv"), "w").write("\n".join(lines) + "\n")
     sys.exit(0)
 eng.stamp(canvas, model.image, 150, lat, None, composite=True, out_f32=out)
 torch.cuda.synchronize()

@@ -190,6 +190,32 @@ def test_conv3x3_with_fused_shortcut(n, H, W, c2, cs0, cs1, cout, BN, splits):
     assert rel_l2(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,BN", [(3, 8, 8, 64, 128, 0), (3, 16, 16, 128, 320, 320 | PAIR), (2, 32, 32, 64, 192, 128),
+                                               (1, 16, 16, 192, 64, 64), (3, 32, 32, 640, 640, 0), (5, 8, 8, 128, 320, 256 | PAIR),
+                                               (1, 64, 64, 512, 512, 0)])
+def test_upsample_conv_folded(n, H, W, cin, cout, BN):
+    """Upsample2D = nearest 2x + conv3x3 as ONE contraction over the half-resolution input: four parity classes of 2x2 taps
+    with pre-summed weights (reference graph: resize folded, models.py:128-186)"""
+    L = nat.lib()
+    x = h(rnd(n, H, W, cin))
+    w = h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=3))
+    bias = rnd(cout, seed=5)
+    wst = torch.empty(4 * cout, 4 * cin, device=DEV, dtype=torch.float16)
+    out = torch.full((n, 2 * H, 2 * W, cout), float("nan"), device=DEV, dtype=torch.float16)
+    rc = L.dtp_op_upconv2x(nat.ptr(x), cin, n, H, W, nat.ptr(w), cout, nat.ptr(bias), nat.ptr(wst), nat.ptr(out), BN,
+                           nat.stream_ptr())
+    nat.check_op(rc, "upconv2x")
+    torch.cuda.synchronize()
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    ref = conv_ref(up, w, cin, bias)
+    assert rel_l2(out, ref) < 2e-3
+    # against the two-kernel path of the same library (upsample kernel + 3x3 contraction): same fp16 inputs, fp32 accumulate
+    up16 = torch.empty(n, 2 * H, 2 * W, cin, device=DEV, dtype=torch.float16)
+    nat.check_op(L.dtp_op_upsample2x(nat.ptr(x), n, H, W, cin, nat.ptr(up16), nat.stream_ptr()), "upsample2x")
+    two = conv_op(up16, w, bias=bias)
+    assert rel_l2(out, two) < 1.5e-3
+
+
 def test_conv3x3_small_cout_f32_nchw():
     n, H, W, cin, cout = 3, 16, 16, 320, 4
     x, w, b = h(rnd(n, H, W, cin)), h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5)), rnd(cout)

@@ -321,7 +321,17 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     eng.set_option("fuse_cross", 0)   # cross-attention as two contractions (scores with softmax epilogue, output)
     outs["cross_two_kernels"] = model.generate(canvas, init_latents=lat, **settings).clone()
     eng.set_option("fuse_cross", 1)
-    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate", "cross_two_kernels"):
+    model.generate(canvas, init_latents=lat, **settings)  # defaults again: at this size no upsample is folded
+    n_ops = eng.counter("unet_plan_ops")
+    eng.set_option("fold_upsample_rows", 0)   # nearest-2x upsample folded into its convolution at every level
+    outs["upsample_folded"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    assert eng.counter("unet_plan_ops") == n_ops - 3  # three upsample launches fewer
+    eng.set_option("fold_upsample", 0)        # ... and at none
+    outs["upsample_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("fold_upsample", 1)
+    eng.set_option("fold_upsample_rows", 3072)
+    for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate", "cross_two_kernels",
+              "upsample_folded", "upsample_separate"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
