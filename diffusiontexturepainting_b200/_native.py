@@ -16,6 +16,7 @@ _OPS = {
     "dtp_op_linear": [vp, i32, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, i32, i32, f32, i32, i32, i32, vp],
     "dtp_op_conv3x3": [vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, i32, i32, vp],
     "dtp_op_conv3x3_shortcut": [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp, i32, i32, vp],
+    "dtp_op_conv3x3_s2": [vp, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, vp],
     "dtp_op_upconv2x": [vp, i32, i32, i32, i32, vp, i32, vp, vp, vp, i32, vp],
     "dtp_op_bmm": [vp, i32, i64, i64, vp, i32, i64, i64, i32, i32, i32, i32, i32, i32, vp, i32, i64, i64, f32, i32, i32,
                    vp],

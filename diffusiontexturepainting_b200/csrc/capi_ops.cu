@@ -111,6 +111,20 @@ int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, con
     return finish(op, r, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
 }
 
+int dtp_op_conv3x3_s2(const void* A, int C, int Nimg, int H, int W, const void* Wt, int Cout, const float* bias, int pad_lo,
+                      void* out, int BN, int splits, void* stream) {
+    GemmOp op;
+    if (BN <= 0) {
+        GemmOp probe;
+        int r0 = gemm_setup_conv3x3_s2(&probe, (const __half*)A, C, Nimg, H, W, (const __half*)Wt, Cout, pad_lo, 128, 1);
+        if (r0) return finish(probe, r0, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+        gemm_pick_config(probe.grid_m, Cout, probe.p.num_kb, (probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0,
+                         &BN, &splits);
+    }
+    int r = gemm_setup_conv3x3_s2(&op, (const __half*)A, C, Nimg, H, W, (const __half*)Wt, Cout, pad_lo, BN, splits);
+    return finish(op, r, bias, nullptr, 0, out, Cout, 0, 1.0f, 0, (cudaStream_t)stream);
+}
+
 int dtp_op_upconv2x(const void* A, int C, int Nimg, int H, int W, const void* Wt, int Cout, const float* bias, void* wstack,
                     void* out, int BN, void* stream) {
     if (Wt != nullptr && launch_upconv_fold_weights((const __half*)Wt, Cout, C, (__half*)wstack, (cudaStream_t)stream)) return -1;

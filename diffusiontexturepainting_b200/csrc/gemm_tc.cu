@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(320, OCC)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
-        if (p.sc_blocks > 0) {
+        if (p.sc_blocks > 0 || p.down2) {
             tma_prefetch_desc(&mapA2);
             tma_prefetch_desc(&mapA3);
         }
@@ -500,7 +500,12 @@ __global__ void __launch_bounds__(320, OCC)
                             ky = (tap >> 1) + (c.z1 >> 1);
                             kx = (tap & 1) + (c.z1 & 1);
                         }
-                        if (tap >= 9) {
+                        if (p.down2) {
+                            const int oy = ky - p.down_pad, ox = kx - p.down_pad;
+                            const int py = oy & 1, px = ox & 1;
+                            const CUtensorMap* mv = py ? (px ? &mapA3 : &mapA2) : (px ? &mapA1 : &mapA0);
+                            tma4<CL>(sa, mv, &full_bar[stage], cb * 64, c.x0 + ((ox - px) >> 1), c.y0 + ((oy - py) >> 1), c.img0);
+                        } else if (tap >= 9) {
                             // fused 1x1 shortcut: unshifted boxes of the shortcut's own sources
                             const int sb = kb - 9 * p.cblocks;
                             if (sb < p.sc_blocks0)
@@ -1251,6 +1256,70 @@ int gemm_setup_conv3x3(GemmOp* op, const __half* A0, int C0, const __half* A1, i
         const int rb = map_blocked(&op->mapB, Wt, (uint64_t)9 * C, Cout, BN);
         op->mapBL = op->mapB;
         return rb;
+    }
+    int rm = 0;
+    if (BN > 256)
+        op->mapB = op->mapBh;
+    else
+        rm = map_rows(&op->mapB, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
+    if (rm) return rm;
+    return setup_ragged(op, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN);
+}
+
+int gemm_setup_conv3x3_s2(GemmOp* op, const __half* A, int C, int Nimg, int H, int W, const __half* Wt, int Cout, int pad_lo,
+                          int BN, int splits) {
+    params_defaults(op->p);
+    GemmParams& p = op->p;
+    const bool want_pair = (BN & GEMM_BN_PAIR) != 0 || gemm_cluster_enabled();
+    BN = fix_bn(BN & ~GEMM_BN_PAIR);
+    if (BN == 320 && !(want_pair && Cout % 320 == 0)) BN = 256;
+    if ((C % 64) != 0 || (H & 1) || (W & 1)) {
+        snprintf(g_gemm_err, sizeof(g_gemm_err), "conv3x3 stride 2 needs C %% 64 == 0 and even H, W (C=%d H=%d W=%d)", C, H, W);
+        return -11;
+    }
+    const int Ho = H / 2, Wo = W / 2;
+    const int KT = 9 * C;
+    p.M = Nimg * Ho * Wo;
+    p.N = Cout;
+    p.mode = 1;
+    p.down2 = 1;
+    p.down_pad = pad_lo ? 1 : 0;
+    p.H = Ho;
+    p.W = Wo;
+    p.Nimg = Nimg;
+    p.bw = largest_divisor_le(Wo, 128);
+    p.bh = largest_divisor_le(Ho, 128 / p.bw);
+    p.bn = (p.bh == Ho) ? (128 / (p.bw * p.bh)) : 1;
+    if (p.bn > Nimg) p.bn = Nimg;
+    if (p.bn < 1) p.bn = 1;
+    p.tiles_x = Wo / p.bw;
+    p.tiles_y = Ho / p.bh;
+    p.rows_valid = p.bw * p.bh * p.bn;
+    p.cblocks0 = C / 64;
+    p.cblocks = C / 64;
+    p.num_kb = 9 * p.cblocks;
+    p.splits = splits < 1 ? 1 : (splits > p.num_kb ? p.num_kb : splits);
+    bind_ctx(op);
+    p.ldc = Cout;
+    op->BN = BN;
+    op->grid_m = p.tiles_x * p.tiles_y * ((Nimg + p.bn - 1) / p.bn);
+    if (BN == 320 && op->grid_m < 2) {
+        BN = 256;
+        op->BN = 256;
+    }
+    CUtensorMap* views[4] = {&op->mapA0, &op->mapA1, &op->mapA2, &op->mapA3};
+    for (int v = 0; v < 4; ++v) {  // view (py, px): pixels (2y + py, 2x + px)
+        const int py = v >> 1, px = v & 1;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)Nimg};
+        uint64_t st[3] = {(uint64_t)C * 4, (uint64_t)C * 4 * W, (uint64_t)C * 2 * W * H};
+        uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+        int r = make_map_4d(views[v], A + (static_cast<size_t>(py) * W + px) * C, dims, st, box);
+        if (r) return r;
+    }
+    op->cluster = 1;
+    if (want_pair && op->grid_m >= 2 && BN >= 32) {
+        if (map_rows(&op->mapBh, Wt, (uint64_t)KT, Cout, (uint64_t)KT, BN > 256 ? BN / 4 : BN / 2)) return -13;
+        op->cluster = 2;
     }
     int rm = 0;
     if (BN > 256)

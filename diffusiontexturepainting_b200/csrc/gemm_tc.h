@@ -93,6 +93,11 @@ struct GemmParams {
     // (py, px); the class's four 2x2 taps read the HALF-resolution input at (y + sy - 1 + py, x + sx - 1 + px); weight rows of
     // class z1 start at z1 * N; output pixel = (2y + py, 2x + px) of the (2H, 2W) image
     int up2;
+    // ---- 3x3 stride-2 convolution without an im2col buffer (gemm_setup_conv3x3_s2): the four tensor maps mapA0..mapA3 are the
+    // (row parity, column parity) views of the input at half resolution; tap (ky, kx) reads input pixel
+    // (2y + ky - down_pad, 2x + kx - down_pad) = view ((ky - down_pad) & 1, (kx - down_pad) & 1) at (y + floor(.../2), x + ...)
+    int down2;     // 1 = on
+    int down_pad;  // 1: symmetric padding 1 (UNet Downsample2D), 0: F.pad (0,1,0,1) (VAE encoder)
 };
 
 struct GemmOp {
@@ -118,6 +123,10 @@ int make_map_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const 
 // tensor): A [Nimg, H, W, C] fp16 NHWC (C % 64 == 0), Wstack [4 * Cout, 4 * C] from launch_upconv_fold_weights, output
 // [Nimg, 2H, 2W, ldc]. One launch, batch coordinate z1 = parity class.
 int gemm_setup_upconv2x(GemmOp* op, const __half* A, int C, int Nimg, int H, int W, const __half* Wstack, int Cout, int BN);
+// 3x3 stride-2 convolution (Downsample2D) straight from the NHWC input [Nimg, H, W, C] (H, W even, C % 64 == 0): output
+// [Nimg, H/2, W/2, Cout]; Wt [Cout, 9*C] as for gemm_setup_conv3x3. pad_lo as in GemmParams::down_pad.
+int gemm_setup_conv3x3_s2(GemmOp* op, const __half* A, int C, int Nimg, int H, int W, const __half* Wt, int Cout, int pad_lo,
+                          int BN, int splits);
 int gemm_setup_linear(GemmOp* op, const __half* A0, int lda0, int K0, const __half* A1, int lda1, int K1, int M,
                       const __half* Wt, int ldw, int N, int BN, int splits, int w_blocked = 0);
 // 3x3/s1/p1 conv over NHWC activations: sources (Nimg,H,W,C0) and optional (Nimg,H,W,C1), C0,C1 % 64 == 0;

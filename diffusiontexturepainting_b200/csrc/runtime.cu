@@ -590,7 +590,6 @@ struct Builder {
     Act downsample(const Act& x, const std::string& p, int pad_lo) {
         if (!ok) return Act{};
         const int Ho = x.H / 2, Wo = x.W / 2;
-        Act col = alloc(x.N, Ho, Wo, 9 * x.C);
         int cout = 0, kk = 0;
         const __half* W = W16(p + ".weight", &cout, &kk);
         if (!ok) return Act{};
@@ -598,6 +597,30 @@ struct Builder {
             fail("downsample weight '" + prefix + p + "' has unexpected K");
             return Act{};
         }
+        if (e.opt_fold_downsample_ && (x.C % 64) == 0 && (x.H % 2) == 0 && (x.W % 2) == 0) {
+            // the nine taps straight from the input through four parity-view tensor maps: no im2col buffer, no gather launch
+            Act out = alloc(x.N, Ho, Wo, cout);
+            if (!ok) return out;
+            GemmOp probe, op;
+            if (gemm_setup_conv3x3_s2(&probe, x.p, x.C, x.N, x.H, x.W, W, cout, pad_lo, 128, 1)) {
+                fail(std::string("stride-2 conv setup: ") + gemm_last_error());
+                return out;
+            }
+            int BN, splits;
+            const int hint = (probe.grid_m >= 2 && gemm_cluster_enabled()) ? GEMM_HINT_CL2 : 0;
+            if (!gemm_tuned_config(probe.grid_m, cout, probe.p.num_kb, hint, &BN, &splits))
+                gemm_pick_config(probe.grid_m, cout, probe.p.num_kb, hint, &BN, &splits);
+            if (gemm_setup_conv3x3_s2(&op, x.p, x.C, x.N, x.H, x.W, W, cout, pad_lo, BN, splits)) {
+                fail(std::string("stride-2 conv setup: ") + gemm_last_error());
+                return out;
+            }
+            op.p.bias = F32(p + ".bias");
+            op.p.out = out.p;
+            op.p.ldc = cout;
+            push_gemm(op, "conv3x3s2");
+            return out;
+        }
+        Act col = alloc(x.N, Ho, Wo, 9 * x.C);
         Engine* eng = &e;
         const __half* xp = x.p;
         __half* cp = col.p;
@@ -2295,6 +2318,14 @@ int Engine::set_option(const char* name, int value) {
     if (n == "fuse_ff_out") {
         opt_fuse_ff_out_ = value;
         unet_plan_.clear();
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "fold_downsample") {
+        opt_fold_downsample_ = value;
+        unet_plan_.clear();
+        vae_enc_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();
         return 0;

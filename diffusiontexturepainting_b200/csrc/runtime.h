@@ -247,6 +247,7 @@ class Engine {
     std::unordered_map<std::string, FusedShortcut> fused_sc_;
     int opt_fuse_shortcut_ = 1;
     std::unordered_map<std::string, __half*> upconv_w_;
+    int opt_fold_downsample_ = 1;        // stride-2 convolutions read the input through parity-view tensor maps (no im2col buffer)
     int opt_fold_upsample_ = 1;          // nearest-2x upsample folded into its convolution (gemm_setup_upconv2x)
     int opt_fold_upsample_rows_ = 3072;  // ... for outputs of at least this many pixels (below, the 16/9 larger folded weights cost more than the multiply-adds save)
     int opt_fold_ln_ = 1;

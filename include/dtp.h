@@ -71,6 +71,10 @@ int dtp_op_conv3x3(const void* A0, int C0, const void* A1, int C1, int Nimg, int
  * rows appended along K), bias = conv2.bias + conv_shortcut.bias (diffusers ResnetBlock2D.forward: output = shortcut(x) + h) */
 int dtp_op_conv3x3_shortcut(const void* A0, int C0, const void* S0, int CS0, const void* S1, int CS1, int Nimg, int H, int W,
                             const void* Wt, int Cout, const float* bias, void* out, int BN, int splits, void* stream);
+/* Downsample2D: conv 3x3 stride 2 straight from the NHWC input (four parity-view tensor maps, no im2col buffer). A (Nimg,H,W,C)
+ * f16, H and W even; pad_lo = 1: padding 1 (UNet), 0: F.pad (0,1,0,1) then no padding (VAE encoder); out (Nimg,H/2,W/2,Cout). */
+int dtp_op_conv3x3_s2(const void* A, int C, int Nimg, int H, int W, const void* Wt, int Cout, const float* bias, int pad_lo,
+                      void* out, int BN, int splits, void* stream);
 /* Upsample2D (diffusers: F.interpolate(scale_factor=2, mode="nearest") then conv 3x3 pad 1; the reference's graph folds the
  * resize, models.py:128-186) as ONE contraction over the half-resolution input: four output-parity classes, each a 2x2
  * convolution with pre-summed taps (4/9 of the multiply-adds, no upsampled tensor). A (Nimg,H,W,C) NHWC f16, Wt [Cout, 9*C]
@@ -176,7 +180,7 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
  * vae, composite; device time and count accumulated since dtp_set_option("stage_timers", 1)).
  * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fuse_cross" (image-token cross-attention as one
  * launch), "fold_ln" (LayerNorm folded into the consuming contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside
- * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "fold_upsample" (nearest-2x upsample
+ * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "fold_downsample" (stride-2 convolutions without an im2col buffer), "fold_upsample" (nearest-2x upsample
  * folded into its 3x3 convolution; "fold_upsample_rows": smallest output pixel count it applies to), "flash", "profile" (per-op events),
  * "stage_timers", "nvtx" (NVTX ranges per stage), "arena_mib" (grow the activation arena to at least this size). */
 long long dtp_get_counter(dtp_handle* h, const char* name);

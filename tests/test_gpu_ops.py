@@ -216,6 +216,29 @@ def test_upsample_conv_folded(n, H, W, cin, cout, BN):
     assert rel_l2(out, two) < 1.5e-3
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout,pad_lo,BN,splits", [(3, 16, 16, 64, 128, 1, 0, 1), (3, 64, 64, 320, 320, 1, 0, 1),
+                                                             (2, 32, 32, 128, 128, 0, 128, 1), (3, 8, 8, 256, 640, 1, 320 | PAIR, 4),
+                                                             (1, 64, 64, 128, 128, 0, 64, 2), (5, 4, 4, 128, 192, 1, 0, 3)])
+def test_conv3x3_stride2_from_parity_views(n, H, W, cin, cout, pad_lo, BN, splits):
+    """Downsample2D without an im2col buffer: tap (ky, kx) is a box of the (row parity, column parity) view of the input"""
+    L = nat.lib()
+    x = h(rnd(n, H, W, cin))
+    w = h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=3))
+    bias = rnd(cout, seed=5)
+    out = torch.full((n, H // 2, W // 2, cout), float("nan"), device=DEV, dtype=torch.float16)
+    rc = L.dtp_op_conv3x3_s2(nat.ptr(x), cin, n, H, W, nat.ptr(w), cout, nat.ptr(bias), pad_lo, nat.ptr(out), BN, splits,
+                             nat.stream_ptr())
+    nat.check_op(rc, "conv3x3_s2")
+    torch.cuda.synchronize()
+    xn = x.float().permute(0, 3, 1, 2)
+    wn = w.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    if pad_lo:
+        ref = F.conv2d(xn, wn, bias, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xn, (0, 1, 0, 1)), wn, bias, stride=2)
+    assert rel_l2(out, ref.permute(0, 2, 3, 1)) < 2e-3
+
+
 def test_conv3x3_small_cout_f32_nchw():
     n, H, W, cin, cout = 3, 16, 16, 320, 4
     x, w, b = h(rnd(n, H, W, cin)), h(rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5)), rnd(cout)

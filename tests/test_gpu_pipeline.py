@@ -330,8 +330,12 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     outs["upsample_separate"] = model.generate(canvas, init_latents=lat, **settings).clone()
     eng.set_option("fold_upsample", 1)
     eng.set_option("fold_upsample_rows", 3072)
+    eng.set_option("fold_downsample", 0)      # stride-2 convolutions as a gather kernel + linear contraction
+    outs["downsample_im2col"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    assert eng.counter("unet_plan_ops") == n_ops + 3
+    eng.set_option("fold_downsample", 1)
     for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate", "cross_two_kernels",
-              "upsample_folded", "upsample_separate"):
+              "upsample_folded", "upsample_separate", "downsample_im2col"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
