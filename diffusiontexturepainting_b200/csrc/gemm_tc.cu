@@ -813,9 +813,11 @@ __global__ void __launch_bounds__(320, OCC)
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                        float* ws = p.workspace +
-                                    ((static_cast<long long>(tile_group(p, c)) * p.splits + c.zsplit) * 128 + r) * BN + cc;
-                        store_f32_chunk(ws, v, 32, true);
+                        const long long widx = ((static_cast<long long>(tile_group(p, c)) * p.splits + c.zsplit) * 128 + r) * BN + cc;
+                        if (p.ws_half)
+                            store_half_chunk(reinterpret_cast<__half*>(p.workspace) + widx, v, 32, true);
+                        else
+                            store_f32_chunk(p.workspace + widx, v, 32, true);
                     }
                 } else if (row >= 0 && !((p.dbg_mode & 1) && raw[0] != 0x7fc01234u)) {
                     float v[32];
@@ -841,11 +843,13 @@ __global__ void __launch_bounds__(320, OCC)
                 // (bit-reproducible) and runs the epilogue for that slice.
                 int* cnt = p.tile_counters + 2 * tile_group(p, c);
                 const int r0 = (c.zsplit * 128) / p.splits, r1 = ((c.zsplit + 1) * 128) / p.splits;
-                const uint32_t slice_bytes = static_cast<uint32_t>(r1 - r0) * BN * 4;
-                const float* wsg = p.workspace + static_cast<long long>(tile_group(p, c)) * p.splits * 128 * BN;
+                const uint32_t esz = p.ws_half ? 2u : 4u;  // partials in fp16 halve the L2 write burst and the gather
+                const uint32_t slice_bytes = static_cast<uint32_t>(r1 - r0) * BN * esz;
+                const uint8_t* wsg = reinterpret_cast<const uint8_t*>(p.workspace) +
+                                     static_cast<long long>(tile_group(p, c)) * p.splits * 128 * BN * esz;
                 // operand stages are idle (this CTA has no further tile): [splits][rows of my slice][BN] staging, then the sums
                 float* stage_f = reinterpret_cast<float*>(smem);
-                float* ssum = stage_f + static_cast<size_t>(p.splits) * (r1 - r0) * BN;
+                float* ssum = reinterpret_cast<float*>(smem + static_cast<size_t>(p.splits) * slice_bytes);
                 if (et == 0) DBG_MARK2(0);
                 fence_proxy_async_all();  // my partial is read by the peers' bulk copies (async proxy)
                 __threadfence();
@@ -867,21 +871,36 @@ __global__ void __launch_bounds__(320, OCC)
                     mbar_arrive_expect_tx(red_bar, static_cast<uint32_t>(p.splits) * slice_bytes);
                     for (int sidx = 0; sidx < p.splits; ++sidx)
                         bulk_load_1d(reinterpret_cast<uint8_t*>(stage_f) + static_cast<size_t>(sidx) * slice_bytes,
-                                     wsg + (static_cast<long long>(sidx) * 128 + r0) * BN, slice_bytes, red_bar);
+                                     wsg + (static_cast<long long>(sidx) * 128 + r0) * BN * esz, slice_bytes, red_bar);
                 }
                 mbar_wait_bounded(red_bar, 0);
                 if (et == 0) DBG_MARK2(4);
                 constexpr int P4 = BN / 4;  // 16-byte pieces per tile row
                 const int npieces = (r1 - r0) * P4;
                 for (int i = et; i < npieces; i += 256) {
-                    const float4* src = reinterpret_cast<const float4*>(stage_f) + i;
-                    float4 a4 = src[0];
-                    for (int sidx = 1; sidx < p.splits; ++sidx) {
-                        const float4 t4 = src[static_cast<size_t>(sidx) * npieces];
-                        a4.x += t4.x;
-                        a4.y += t4.y;
-                        a4.z += t4.z;
-                        a4.w += t4.w;
+                    float4 a4;
+                    if (p.ws_half) {
+                        const uint2* src = reinterpret_cast<const uint2*>(stage_f) + i;
+                        a4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        for (int sidx = 0; sidx < p.splits; ++sidx) {
+                            const uint2 t = src[static_cast<size_t>(sidx) * npieces];
+                            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+                            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+                            a4.x += lo.x;
+                            a4.y += lo.y;
+                            a4.z += hi.x;
+                            a4.w += hi.y;
+                        }
+                    } else {
+                        const float4* src = reinterpret_cast<const float4*>(stage_f) + i;
+                        a4 = src[0];
+                        for (int sidx = 1; sidx < p.splits; ++sidx) {
+                            const float4 t4 = src[static_cast<size_t>(sidx) * npieces];
+                            a4.x += t4.x;
+                            a4.y += t4.y;
+                            a4.z += t4.z;
+                            a4.w += t4.w;
+                        }
                     }
                     // unit u = (row, 32-column chunk) occupies 128 B; its 16-B pieces are XOR-swizzled by the unit index
                     const int rl = i / P4, c4 = i - rl * P4;
@@ -1589,6 +1608,16 @@ static bool splitk_fused(const GemmOp* op) {
     }
     return groups * p.splits <= num_sms();
 }
+// fp16 partials for the in-kernel split-K reduction (each partial is rounded once; the sum stays fp32): on by default
+static int g_splitk_half = -1;  // -1: from the environment (DTP_SPLITK_F16, default on)
+void gemm_set_splitk_half(int on) { g_splitk_half = on ? 1 : 0; }
+static bool splitk_half() {
+    if (g_splitk_half < 0) {
+        const char* e = getenv("DTP_SPLITK_F16");
+        g_splitk_half = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_splitk_half != 0;
+}
 int gemm_num_launches(const GemmOp* op) { return (op->p.splits > 1 && !splitk_fused(op)) ? 2 : 1; }
 
 static int num_sms() {
@@ -1627,6 +1656,7 @@ static int launch_light(const GemmOp* op, cudaStream_t stream) {
     p.total_tiles = static_cast<int>(tiles);
     const int cap = 2 * num_sms();
     p.tile_counters = (tiles <= cap && splitk_fused(op)) ? op->tile_counters : nullptr;
+    p.ws_half = (p.tile_counters != nullptr && splitk_half()) ? 1 : 0;
     const int grid = static_cast<int>(tiles < cap ? tiles : cap);
     cudaError_t e = launch_k(gemm_tc_kernel<BN, STAGES, 1, 2>, dim3(grid), dim3(320), SMEM, stream, op->mapA0, op->mapA1, op->mapB, op->mapBL, op->mapA2, op->mapA3, p);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -1672,6 +1702,7 @@ static int launch_cfg(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     p.tile_counters = splitk_fused(op) ? op->tile_counters : nullptr;
+    p.ws_half = (p.tile_counters != nullptr && splitk_half()) ? 1 : 0;
     cudaError_t e;
     if (cl == 2) {
         const int max_clusters = num_sms() / 2;  // (fused split-K additionally requires tiles <= max_pair_clusters())
@@ -1762,6 +1793,7 @@ static int launch_pair_only(const GemmOp* op, cudaStream_t stream) {
     }
     p.total_tiles = static_cast<int>(tiles);
     p.tile_counters = splitk_fused(op) ? op->tile_counters : nullptr;
+    p.ws_half = (p.tile_counters != nullptr && splitk_half()) ? 1 : 0;
     const int max_clusters = num_sms() / 2;
     const int nclusters = static_cast<int>(tiles < max_clusters ? tiles : max_clusters);
     cudaLaunchConfig_t cfg = {};

@@ -2322,6 +2322,12 @@ int Engine::set_option(const char* name, int value) {
         g_stamp_.key.clear();
         return 0;
     }
+    if (n == "splitk_f16") {
+        gemm_set_splitk_half(value);
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
     if (n == "fold_downsample") {
         opt_fold_downsample_ = value;
         unet_plan_.clear();

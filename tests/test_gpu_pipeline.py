@@ -334,8 +334,11 @@ def test_graph_replay_and_options_are_equivalent(tiny):
     outs["downsample_im2col"] = model.generate(canvas, init_latents=lat, **settings).clone()
     assert eng.counter("unet_plan_ops") == n_ops + 3
     eng.set_option("fold_downsample", 1)
+    eng.set_option("splitk_f16", 0)           # fp32 partials in the in-kernel split-K reduction
+    outs["splitk_f32_partials"] = model.generate(canvas, init_latents=lat, **settings).clone()
+    eng.set_option("splitk_f16", 1)
     for k in ("unfolded", "noflash", "ln_kernels", "ln_folded", "shortcut_separate", "ff_out_separate", "cross_two_kernels",
-              "upsample_folded", "upsample_separate", "downsample_im2col"):
+              "upsample_folded", "upsample_separate", "downsample_im2col", "splitk_f32_partials"):
         e = rel_l2(outs[k], outs["eager"])
         log(f"tiny.variant.{k}", rel_l2=e)
         assert e < 2e-3
