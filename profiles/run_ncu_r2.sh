@@ -16,7 +16,7 @@ gzip -f gpurun_out/launches_r2.csv
 # 2. --set full captures inside a 512x512 stamp
 timeout 600 $NCU --set full --import-source on -k regex:gemm_tc_kernel -s 1200 -c 8 -o gpurun_out/prof_r2_gemm512 -f python profiles/profile_stamp.py --no-op-profile --no-graph --profiler-range > gpurun_out/ncu_full1.log 2>&1; echo rc=$?
 export_rep prof_r2_gemm512
-timeout 600 $NCU --set full --import-source on -k regex:"flash_attn2|gn_fused|layernorm" -s 40 -c 6 -o gpurun_out/prof_r2_misc512 -f python profiles/profile_stamp.py --no-op-profile --no-graph --profiler-range > gpurun_out/ncu_full2.log 2>&1; echo rc=$?
+timeout 600 $NCU --set full --import-source on -k regex:"flash_attn2|gn_fused|gn_group2|cross_attn" -s 40 -c 10 -o gpurun_out/prof_r2_misc512 -f python profiles/profile_stamp.py --no-op-profile --no-graph --profiler-range > gpurun_out/ncu_full2.log 2>&1; echo rc=$?
 export_rep prof_r2_misc512
 # 3. the server's operating point: 256x256, B=1
 timeout 600 $NCU --metrics gpu__time_duration.sum --csv --log-file gpurun_out/launches_r2_256.csv python profiles/profile_stamp.py --resolution 256 --no-op-profile --no-graph --profiler-range > gpurun_out/ncu_list_r2_256.log 2>&1; echo rc=$?; gzip -f gpurun_out/launches_r2_256.csv
