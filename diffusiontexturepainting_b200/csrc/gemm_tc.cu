@@ -1593,21 +1593,6 @@ static void bind_ctx(GemmOp* op) {
 }
 static int num_sms();
 static int max_pair_clusters();
-// The in-kernel split-K reduction waits for the other CTAs of a tile's split group, so it is only used when every CTA owns
-// exactly one tile and the whole grid is co-resident (tiles <= SMs; CTA pairs: <= the co-resident cluster count).
-static bool splitk_fused(const GemmOp* op) {
-    const GemmParams& p = op->p;
-    if (p.splits <= 1 || op->tile_counters == nullptr) return false;
-    const long long gn = (p.N + op->BN - 1) / op->BN;
-    const long long groups = static_cast<long long>(op->grid_m) * gn * p.nz1 * p.nz2;
-    if (2 * groups > kTileCounterSlots) return false;
-    if (op->BN > 256 && p.splits < 4) return false;  // slice staging of the reduction must fit the operand stages
-    if (op->cluster == 2) {
-        const long long pair_tiles = static_cast<long long>((op->grid_m + 1) / 2) * gn * p.nz1 * p.nz2 * p.splits;
-        return pair_tiles <= max_pair_clusters();
-    }
-    return groups * p.splits <= num_sms();
-}
 // fp16 partials for the in-kernel split-K reduction (each partial is rounded once; the sum stays fp32): on by default
 static int g_splitk_half = -1;  // -1: from the environment (DTP_SPLITK_F16, default on)
 void gemm_set_splitk_half(int on) { g_splitk_half = on ? 1 : 0; }
@@ -1617,6 +1602,23 @@ static bool splitk_half() {
         g_splitk_half = (e && e[0] == '0') ? 0 : 1;
     }
     return g_splitk_half != 0;
+}
+// The in-kernel split-K reduction waits for the other CTAs of a tile's split group, so it is only used when every CTA owns
+// exactly one tile and the whole grid is co-resident (tiles <= SMs; CTA pairs: <= the co-resident cluster count).
+static bool splitk_fused(const GemmOp* op) {
+    const GemmParams& p = op->p;
+    if (p.splits <= 1 || op->tile_counters == nullptr) return false;
+    const long long gn = (p.N + op->BN - 1) / op->BN;
+    const long long groups = static_cast<long long>(op->grid_m) * gn * p.nz1 * p.nz2;
+    if (2 * groups > kTileCounterSlots) return false;
+    // slice staging of the reduction must fit the idle operand stages: 128 * BN * (2 | 4) B of partial slices + the fp32 sums of
+    // the CTA's own slice; 320-wide tiles with fp32 partials only fit from 4 splits up, with fp16 partials always
+    if (op->BN > 256 && p.splits < 4 && !splitk_half()) return false;
+    if (op->cluster == 2) {
+        const long long pair_tiles = static_cast<long long>((op->grid_m + 1) / 2) * gn * p.nz1 * p.nz2 * p.splits;
+        return pair_tiles <= max_pair_clusters();
+    }
+    return groups * p.splits <= num_sms();
 }
 int gemm_num_launches(const GemmOp* op) { return (op->p.splits > 1 && !splitk_fused(op)) ? 2 : 1; }
 

@@ -1,7 +1,8 @@
 """One small end-to-end stamp for compute-sanitizer (memcheck / racecheck / synccheck): tiny configuration, B = 2,
 128 x 128, 3 evaluations, eager launches (no graph) so every kernel instantiation the tiny model uses runs under the tool:
-single-CTA and CTA-pair contraction tiles, the in-kernel split-K reduction (tickets), flash attention, the single-launch
-GroupNorm (per-sample barrier), canvas pre-process, composite.
+single-CTA and CTA-pair contraction tiles, the in-kernel split-K reduction (tickets, fp16 partials), the folded upsample and
+stride-2 convolutions, the fused cross-attention kernel, flash attention, both GroupNorm kernels (per-group and per-sample
+barrier), canvas pre-process, composite.
     compute-sanitizer --tool memcheck  python profiles/sanitize_stamp.py
     compute-sanitizer --tool racecheck python profiles/sanitize_stamp.py
 """
@@ -22,6 +23,7 @@ model = TRTConditionalInpainter(R, device=0, model_config=cfg, state_dicts=W.syn
 model.pipeline.sample_posterior = False
 model.pipeline.strict_schedule = True
 model.engine.set_option("graph", 0)
+model.engine.set_option("fold_upsample_rows", 0)  # the folded upsample convolutions too (off at this size by default)
 model.set_brush(smooth_image(1, 3, R))
 canvas = make_canvas(B, R)
 lat = torch.randn(B, 4, R // 8, R // 8, generator=torch.Generator().manual_seed(42))
