@@ -182,6 +182,22 @@ if __name__ == "__main__":
                     (3, 16, 16, 1280, 640, 1280), (3, 16, 16, 1280, 2560, 1280), (3, 16, 16, 1280, 1920, 1280),
                     (3, 8, 8, 1280, 2560, 1280)]:
             sweep_conv_sc(*shp)
+    if which == "splitk":  # every stamp shape with at most 24 row tiles (the split-K candidates), after a change of the reduction
+        for shp in [(3072, 640, 640), (3072, 1920, 640), (3072, 640, 2560), (3072, 640, 1280), (3072, 320, 2880), (768, 1280, 1280),
+                    (768, 3840, 1280), (768, 1280, 5120), (768, 1280, 2560), (768, 640, 5760), (192, 1280, 1280), (192, 1280, 2560),
+                    (192, 1280, 5120), (192, 1280, 11520), (192, 3840, 1280), (3072, 640, 1920), (768, 1280, 1920), (3072, 640, 960),
+                    (768, 1280, 640), (3072, 640, 320), (3072, 640, 3200), (768, 1280, 6400), (192, 1280, 6400)]:
+            sweep_linear(*shp)
+        for shp in [(3072, 5120, 640), (768, 10240, 1280), (192, 10240, 1280)]:
+            sweep_linear(*shp, flags=8)
+        for shp in [(3, 32, 32, 320, 640), (3, 32, 32, 640, 640), (3, 32, 32, 960, 640), (3, 32, 32, 1280, 640), (3, 32, 32, 1920, 640),
+                    (3, 32, 32, 1280, 1280), (3, 16, 16, 640, 1280), (3, 16, 16, 1280, 1280), (3, 16, 16, 1920, 1280),
+                    (3, 16, 16, 2560, 1280), (3, 8, 8, 1280, 1280), (3, 8, 8, 2560, 1280)]:
+            sweep_conv(*shp)
+        for shp in [(3, 32, 32, 640, 320, 640), (3, 32, 32, 640, 1920, 640), (3, 32, 32, 640, 1280, 640), (3, 32, 32, 640, 960, 640),
+                    (3, 16, 16, 1280, 640, 1280), (3, 16, 16, 1280, 2560, 1280), (3, 16, 16, 1280, 1920, 1280),
+                    (3, 8, 8, 1280, 2560, 1280)]:
+            sweep_conv_sc(*shp)
     if which in ("all", "vae"):
         for shp in [(2, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:
             sweep_conv(*shp)
