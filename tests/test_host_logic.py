@@ -147,3 +147,47 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_resize_fold_algebra():
+    """The two resize folds of the launch plan, restated in torch on the CPU (the kernels are checked on the GPU in
+    tests/test_gpu_ops.py): (a) conv3x3(nearest_upsample_2x(x)) == four parity-class 2x2 convolutions over x with the taps
+    that land on the same source pixel pre-summed (kernels.cu upconv_fold_weights_kernel, gemm_setup_upconv2x);
+    (b) a stride-2 3x3 convolution reads tap (ky, kx) from the (row parity, column parity) view of the input shifted by
+    floor((k - pad) / 2) (gemm_setup_conv3x3_s2), for both paddings the model uses."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 6, 8, generator=g, dtype=torch.float64)
+    w = torch.randn(7, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    taps = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}  # S(parity, s): 3x3 taps that share source offset s-1+parity
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    H, W = x.shape[2:]
+    for py in range(2):
+        for px in range(2):
+            acc = 0
+            for sy in range(2):
+                for sx in range(2):
+                    weff = sum(w[:, :, ky, kx] for ky in taps[(py, sy)] for kx in taps[(px, sx)])
+                    oy, ox = sy - 1 + py, sx - 1 + px  # source offset of this tap
+                    src = xp[:, :, 1 + oy:1 + oy + H, 1 + ox:1 + ox + W]
+                    acc = acc + torch.einsum("oc,nchw->nohw", weff, src)
+            out[:, :, py::2, px::2] = acc
+    assert torch.allclose(out, ref, atol=1e-12)
+    for pad in (1, 0):
+        if pad:
+            ref2 = F.conv2d(x, w, stride=2, padding=1)
+        else:
+            ref2 = F.conv2d(F.pad(x, (0, 1, 0, 1)), w, stride=2)
+        Ho, Wo = H // 2, W // 2
+        views = {(py, px): F.pad(x[:, :, py::2, px::2], (1, 1, 1, 1)) for py in range(2) for px in range(2)}  # zero fill = TMA OOB
+        acc = 0
+        for ky in range(3):
+            for kx in range(3):
+                oy, ox = ky - pad, kx - pad
+                py, px = oy & 1, ox & 1
+                sy, sx = (oy - py) >> 1, (ox - px) >> 1
+                src = views[(py, px)][:, :, 1 + sy:1 + sy + Ho, 1 + sx:1 + sx + Wo]
+                acc = acc + torch.einsum("oc,nchw->nohw", w[:, :, ky, kx], src)
+        assert torch.allclose(acc, ref2, atol=1e-12)
