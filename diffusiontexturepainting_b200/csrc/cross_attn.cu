@@ -40,7 +40,8 @@ struct CrossParams {
     const float* ln_colsum;  // [3][128]
     const float* sbias;      // [3][128]  W_score beta (LayerNorm shift seen through the folded query projection)
     const float* obias;      // [C] attn2.to_out.0.bias
-    const __half* h;         // [3 * rows_z, C]: rows in (score operand and residual)
+    const __half* h;         // [3 * rows_z, C]: rows in (score operand and residual); in_fold: [2 * rows_z, C]
+    int in_fold;             // 1: row groups 0 and 1 share their input rows (group z reads input group max(z - 1, 0)); out of place only
     __half* hout;            // result rows; == h (in place) only when csplit == 1
     int csplit;              // the output chunks of a row tile are spread over `csplit` CTAs (grid.z), each recomputing the
                              // tile's scores: parallelism for the narrow levels (6 / 3 row tiles at 16x16 / 8x8 latents)
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(320, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, z = blockIdx.y;
-    const int row0 = z * p.rows_z + m_tile * 128;  // first row of this tile in h
+    const int zi = p.in_fold ? max(z - 1, 0) : z;        // input row group
+    const int row0 = zi * p.rows_z + m_tile * 128;       // first row of this tile in h (operand, residual, LayerNorm statistics)
+    const int row0_out = z * p.rows_z + m_tile * 128;    // ... in hout / stats_out
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(320, 1)
         const int et = threadIdx.x - 64;
         const bool row_ok = m_tile * 128 + r < p.rows_z;
         const long long grow = static_cast<long long>(row0) + r;
+        const long long grow_out = static_cast<long long>(row0_out) + r;
         const uint32_t t_lane = static_cast<uint32_t>(q * 32) << 16;
         // per-brush vectors: independent of the predecessor kernel
         if (et < 128) {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(320, 1)
         if (lane == 0) mbar_arrive(p_full);
         // ---- stage-2 epilogue: chunk by chunk (bias + residual, optional row statistics), in place into h
         const __half* hrow = p.h + grow * p.C;
-        __half* orow = p.hout + grow * p.C;
+        __half* orow = p.hout + grow_out * p.C;
         for (int c = blockIdx.z, ci = 0; c < p.n_chunks; c += p.csplit, ++ci) {
             const int n0 = c * 256;
             cx_epi_sync();  // previous chunk's readers are done with sob
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(320, 1)
                             s0 += v[i];
                             q0 = fmaf(v[i], v[i], q0);
                         }
-                        p.stats_out[static_cast<long long>((n0 + cc) >> 5) * p.stats_rows + grow] = make_float2(s0, q0);
+                        p.stats_out[static_cast<long long>((n0 + cc) >> 5) * p.stats_rows + grow_out] = make_float2(s0, q0);
                     }
                     uint4* op = reinterpret_cast<uint4*>(orow + n0 + cc);
 #pragma unroll
@@ -340,12 +344,17 @@ __global__ void __launch_bounds__(320, 1)
 // h / hout: [3 * rows_z, C] fp16 (hout == h: in place, no chunk split); wscore: [3][128][C]; wout: [3][C][128]
 int cross_attn_setup(CrossOp* op, const __half* h, __half* hout, int rows_z, int C, int T, const __half* wscore,
                      const __half* wout, const float2* ln_stats, const float* ln_colsum, const float* sbias, const float* obias,
-                     float2* stats_out) {
+                     float2* stats_out, int in_fold) {
     if ((C % 64) != 0 || C < 64 || T < 1 || T > 16 || rows_z < 1) {
         snprintf(g_cross_err, sizeof(g_cross_err), "cross_attn: unsupported shape rows=%d C=%d T=%d", rows_z, C, T);
         return -1;
     }
-    const uint64_t rows = 3ull * rows_z;
+    if (in_fold && hout == h) {
+        snprintf(g_cross_err, sizeof(g_cross_err), "cross_attn: shared input row groups need an out-of-place result");
+        return -1;
+    }
+    op->in_fold = in_fold ? 1 : 0;
+    const uint64_t rows = (in_fold ? 2ull : 3ull) * rows_z;
     {
         uint64_t dims[4] = {(uint64_t)C, rows, 1, 1};
         uint64_t st[3] = {(uint64_t)C * 2, (uint64_t)C * 2 * rows, (uint64_t)C * 2 * rows};
@@ -401,7 +410,8 @@ int cross_attn_launch(const CrossOp* op, cudaStream_t st) {
     p.kb1 = op->C / 64;
     p.ln_stats = op->ln_stats;
     p.ln_chunks = op->C / 32;
-    p.ln_rows = 3 * op->rows_z;
+    p.ln_rows = (op->in_fold ? 2 : 3) * op->rows_z;
+    p.in_fold = op->in_fold;
     p.ln_inv_c = 1.0f / static_cast<float>(op->C);
     p.ln_eps = 1e-5f;
     p.ln_colsum = op->ln_colsum;

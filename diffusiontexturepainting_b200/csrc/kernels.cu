@@ -1341,6 +1341,24 @@ int launch_guidance_ddim(const float* eps3, const float* latents_in, float* late
     return check_launch("guidance_ddim");
 }
 
+__global__ void __launch_bounds__(256) expand_branches_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long grp_vec) {
+    pdl_enter();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // vector of the 3-group output
+    if (i >= 3 * grp_vec) return;
+    out[i] = in[i < grp_vec ? i : i - grp_vec];
+}
+int launch_expand_branches(const __half* in, __half* out, int Bs, long long per_sample, cudaStream_t st) {
+    const long long grp = static_cast<long long>(Bs) * per_sample;
+    if ((grp & 7) || (reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+        snprintf(g_kerr, sizeof(g_kerr), "expand_branches: group size / pointers must be 16-byte multiples");
+        return -1;
+    }
+    const long long grp_vec = grp / 8;
+    launch_k(expand_branches_kernel, dim3(static_cast<unsigned>((3 * grp_vec + 255) / 256)), dim3(256), 0, st,
+             reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), grp_vec);
+    return check_launch("expand_branches");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // layout packers
 // ------------------------------------------------------------------------------------------------------------

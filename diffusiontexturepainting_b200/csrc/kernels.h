@@ -61,13 +61,16 @@ struct CrossOp {
     __half* hout;
     int csplit;
     float2* stats_out;
+    int in_fold;  // row groups 0 and 1 read the same input rows (h has two row groups, hout three)
 };
 int cross_attn_setup(CrossOp* op, const __half* h, __half* hout, int rows_z, int C, int T, const __half* wscore,
                      const __half* wout, const float2* ln_stats, const float* ln_colsum, const float* sbias, const float* obias,
-                     float2* stats_out);
+                     float2* stats_out, int in_fold = 0);
 int cross_attn_launch(const CrossOp* op, cudaStream_t st);
 const char* cross_last_error();
 
+// [cond | texture-guidance] sample groups (Bs samples each, per_sample halfs per sample) -> [uncond = cond | cond | texture-guidance]
+int launch_expand_branches(const __half* in, __half* out, int Bs, long long per_sample, cudaStream_t st);
 int launch_upsample2x(const __half* x, int Nimg, int H, int W, int C, __half* out, cudaStream_t st);
 // stride-2 3x3 gather: out[(n,oy,ox)][tap*C + c] = x[n, 2*oy+ky-pad_lo, 2*ox+kx-pad_lo, c] (0 outside)
 int launch_im2col_s2(const __half* x, int Nimg, int H, int W, int C, int pad_lo, int Ho, int Wo, __half* out,

@@ -1105,12 +1105,19 @@ int Engine::prepare_ln_fold() {
 // ------------------------------------------------------------------------------------------------------------
 // UNet plan
 // ------------------------------------------------------------------------------------------------------------
+// dedup: the uncond and the cond branch of a stamp see the same UNet sample input and differ only in their cross-attention
+// context (inpaint_pipeline.py:116-138: mask = [m, m, ctx_m], masked_latents = [l, l, ctx_l], embeddings = [neg, prompt,
+// prompt]), so everything in front of the FIRST cross-attention of the network is computed once for both: x then holds the
+// samples [cond | texture-guidance] only, the fused cross-attention kernel reads row group max(z - 1, 0) and writes all three
+// groups, and the block returns [uncond | cond | texture-guidance]. Exact (the two branches were bitwise equal before).
 static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std::string& p, const Act& x, __half* kv,
-                         const int* kv_index) {
+                         const int* kv_index, bool dedup = false) {
     if (!b.ok) return Act{};
     const int C = x.C, heads = cfg.unet_heads, d = C / heads;
     const int seq = x.H * x.W, batch = x.N;
     const long long rows = x.rows();
+    const int batch_out = dedup ? batch / 2 * 3 : batch;
+    const long long rows_out = dedup ? rows / 2 * 3 : rows;
     const std::string t = p + ".transformer_blocks.0";
     const int tf = e.tf_index(p);
     // The three LayerNorms of the block are folded into the contractions that consume them (gemm_tc.h; the reference fuses
@@ -1120,8 +1127,27 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
     // The GEGLU contraction is epilogue-bound at the wide levels (6.5 tiles of 128 x 256 per CTA at 12 288 rows): there the
     // folded epilogue costs more than the LayerNorm kernel it removes (measured +12 us vs -10.5 us), so norm3 is folded
     // only below fold_ln_ff_rows rows (norm1 / norm2 are folded everywhere: QKV +6 us / scores +2.5 us vs -10.5 us each)
-    const bool fl3 = fl && rows <= e.fold_ln_ff_rows();
+    const bool fl3 = fl && rows_out <= e.fold_ln_ff_rows();
     float2* st = fl ? static_cast<float2*>(b.raw(static_cast<size_t>(rows) * (C / 32) * sizeof(float2))) : nullptr;
+    // dedup: the row statistics behind the cross-attention are laid out for three row groups
+    float2* st3 = (dedup && fl3) ? static_cast<float2*>(b.raw(static_cast<size_t>(rows_out) * (C / 32) * sizeof(float2))) : st;
+    Act x3 = x;  // residual of the block's output
+    if (dedup && b.ok) {
+        x3 = b.alloc(batch_out, x.H, x.W, C);
+        if (!b.ok) return Act{};
+        Engine* eng = &e;
+        const __half* src = x.p;
+        __half* dst = x3.p;
+        const int Bs = batch / 2;
+        const long long per_sample = static_cast<long long>(seq) * C;
+        b.plan.add(K_OTHER, [=](cudaStream_t s) -> int {
+            if (launch_expand_branches(src, dst, Bs, per_sample, s)) {
+                eng->set_error(kernels_last_error());
+                return -1;
+            }
+            return 1;
+        }, "expand_branches");
+    }
     Act n = b.groupnorm(x, Act{}, p + ".norm", 1e-6f, 0);
     Act h = b.like(x, C);
     int wr = 0, wc = 0;
@@ -1176,13 +1202,14 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
     if (fl && e.fuse_cross() && heads * 16 == 128 && (C % 64) == 0) {
         // score and output contraction as ONE kernel: the probabilities stay in shared memory (cross_attn.cu)
         CrossOp cop;
-        const long long grp_rows = rows / 3;
+        const long long grp_rows = dedup ? rows / 2 : rows / 3;
         // few row tiles (narrow levels): out of place, so that the output chunks can be spread over CTAs
-        const bool split = ((grp_rows + 127) / 128) * 3 * 2 <= 148 && C > 256;
-        Act h2 = split ? b.like(x, C) : h;
+        const bool split = dedup || (((grp_rows + 127) / 128) * 3 * 2 <= 148 && C > 256);
+        Act h2 = split ? b.alloc(batch_out, x.H, x.W, C) : h;
         if (!b.ok) return Act{};
         if (cross_attn_setup(&cop, h.p, h2.p, static_cast<int>(grp_rows), C, T, e.ln(tf).wscore, e.wout(tf), st,
-                             e.ln(tf).ws_cs, e.ln(tf).ws_b, b.F32(t + ".attn2.to_out.0.bias"), fl3 ? st : nullptr)) {
+                             e.ln(tf).ws_cs, e.ln(tf).ws_b, b.F32(t + ".attn2.to_out.0.bias"), fl3 ? st3 : nullptr,
+                             dedup ? 1 : 0)) {
             b.fail(std::string("cross attention setup: ") + cross_last_error());
         } else if (b.ok) {
             Engine* eng = &e;
@@ -1199,6 +1226,9 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
             b.release(h);
             h = h2;
         }
+    } else if (dedup) {
+        b.fail("branch de-duplication needs the fused cross-attention kernel");
+        return Act{};
     } else if (e.fold_cross()) {
         const int HP = heads * 16;
         const long long grp_rows = rows / 3;
@@ -1251,36 +1281,36 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         }
         b.release(att);
     }
-    // GEGLU feed-forward
+    // GEGLU feed-forward (from here on every tensor has the output's sample count)
     if (!fl3) {
-        tmp = b.like(x, C);
+        tmp = b.like(h, C);
         b.layernorm(h, t + ".norm3", tmp.p);
     }
-    Act g = b.like(x, 4 * C);
+    Act g = b.like(h, 4 * C);
     {
         Lin l;
-        l.A0 = fl3 ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows;
+        l.A0 = fl3 ? h.p : tmp.p; l.lda0 = C; l.K0 = C; l.M = rows_out;
         l.W = fl3 ? e.ln(tf).ff1_w : b.W16(t + ".ff.net.0.proj.weight"); l.ldw = C; l.N = 8 * C;
         l.bias = fl3 ? e.ln(tf).ff1_b : b.F32(t + ".ff.net.0.proj.bias"); l.out = g.p; l.ldc = 4 * C; l.flags = EPI_GEGLU;
         if (fl3) {
-            l.ln_stats = st; l.ln_colsum = e.ln(tf).ff1_cs; l.ln_C = C;
+            l.ln_stats = st3; l.ln_colsum = e.ln(tf).ff1_cs; l.ln_C = C;
         }
         b.linear(l);
     }
     if (!fl3) b.release(tmp);
-    Act out = b.like(x, C);
+    Act out = b.like(h, C);
     if (e.fuse_ff_out()) {
         // ff.net.2 + residual + proj_out + residual as ONE contraction over [g | h] (runtime.h, FfOut)
         Lin l;
-        l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.A1 = h.p; l.lda1 = C; l.K1 = C; l.M = rows;
+        l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.A1 = h.p; l.lda1 = C; l.K1 = C; l.M = rows_out;
         l.W = e.ffo(tf).W; l.ldw = 5 * C; l.N = C; l.bias = e.ffo(tf).bias;
-        l.res = x.p; l.ldr = C; l.out = out.p; l.tune_kb = 4 * C / 64;
+        l.res = x3.p; l.ldr = C; l.out = out.p; l.tune_kb = 4 * C / 64;
         b.linear(l);
         b.release(g);
     } else {
         {
             Lin l;
-            l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows;
+            l.A0 = g.p; l.lda0 = 4 * C; l.K0 = 4 * C; l.M = rows_out;
             l.W = b.W16(t + ".ff.net.2.weight"); l.ldw = 4 * C; l.N = C;
             l.bias = b.F32(t + ".ff.net.2.bias"); l.res = h.p; l.ldr = C; l.out = h.p;
             b.linear(l);
@@ -1288,19 +1318,24 @@ static Act transformer2d(Builder& b, Engine& e, const dtp_config& cfg, const std
         b.release(g);
         {
             Lin l;
-            l.A0 = h.p; l.lda0 = C; l.K0 = C; l.M = rows;
+            l.A0 = h.p; l.lda0 = C; l.K0 = C; l.M = rows_out;
             l.W = b.W16(p + ".proj_out.weight"); l.ldw = C; l.N = C;
-            l.bias = b.F32(p + ".proj_out.bias"); l.res = x.p; l.ldr = C; l.out = out.p;
+            l.bias = b.F32(p + ".proj_out.bias"); l.res = x3.p; l.ldr = C; l.out = out.p;
             b.linear(l);
         }
     }
     b.release(h);
+    if (dedup) b.release(x3);
+    if (st3 && st3 != st) b.release_raw(st3);
     if (st) b.release_raw(st);
     return out;
 }
 
-int Engine::build_unet_plan(int B, int R) {
-    if (unet_plan_.key_a == B && unet_plan_.key_b == R) return 0;
+// shared_input: the sample groups [uncond | cond] of the evaluation are known to be identical (the stamp path packs them from
+// the same latents / mask / masked-image latents); false for dtp_unet_forward with a caller-supplied sample tensor
+int Engine::build_unet_plan(int B, int R, bool shared_input) {
+    const bool want_dedup = shared_input && opt_dedup_branches_ != 0;
+    if (unet_plan_.key_a == B && unet_plan_.key_b == R && unet_plan_dedup_ == want_dedup) return 0;
     if (R % 8) return fail("resolution must be a multiple of 8");
     if (ensure_arena()) return -1;
     const int Bz = 3 * B, h = R / 8;
@@ -1347,9 +1382,18 @@ int Engine::build_unet_plan(int B, int R) {
     for (int i = 0; i < 4 && b.ok; ++i) {
         for (int j = 0; j < cfg_.unet_layers_per_block && b.ok; ++j) {
             const std::string rp = "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
-            Act y = res(rp, x, Act{});
+            // first resnet + first self-attention: once for the uncond and the cond branch (transformer2d, dedup)
+            const bool dd = i == 0 && j == 0 && want_dedup && cfg_.unet_down_attn[0] && fold_ln() && fold_cross() &&
+                            fuse_cross() && cfg_.unet_heads * 16 == 128 && (x.C % 64) == 0;
+            Act xin = x;
+            if (dd) {
+                xin.p = x.p + static_cast<size_t>(B) * h * h * x.C;  // samples [cond | texture-guidance] of conv_in's output
+                xin.N = 2 * B;
+            }
+            Act y = res(rp, xin, Act{});
             if (cfg_.unet_down_attn[i]) {
-                Act z = tf("down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), y);
+                const std::string ap = "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j);
+                Act z = dd ? transformer2d(b, *this, cfg_, ap, y, cross_kv_[tf_idx[ap]], kv_index_, true) : tf(ap, y);
                 b.release(y);
                 y = z;
             }
@@ -1401,6 +1445,7 @@ int Engine::build_unet_plan(int B, int R) {
     }
     unet_plan_.key_a = B;
     unet_plan_.key_b = R;
+    unet_plan_dedup_ = want_dedup;
     return ensure_ws();
 }
 
@@ -2006,7 +2051,7 @@ int Engine::unet_forward(int B, int R, const float* sample, const float* latents
     if (!cond_set_) return fail("unet_forward: call dtp_set_condition first");
     if (step < 0 || step >= n_steps_) return fail("unet_forward: step outside the schedule");
     if (build_temb_tables(st)) return -1;
-    if (build_unet_plan(B, R)) return -1;
+    if (build_unet_plan(B, R, sample == nullptr)) return -1;
     const int h = R / 8, Bz = 3 * B;
     if (sample) {
         KCHECK(launch_nchw_to_nhwc_pad(sample, Bz, cfg_.unet_in_channels, h * h, 64, 1.0f, unet_in_, st));
@@ -2324,6 +2369,13 @@ int Engine::set_option(const char* name, int value) {
     }
     if (n == "splitk_f16") {
         gemm_set_splitk_half(value);
+        g_infer_.key.clear();
+        g_stamp_.key.clear();
+        return 0;
+    }
+    if (n == "dedup_branches") {
+        opt_dedup_branches_ = value;
+        unet_plan_.clear();
         g_infer_.key.clear();
         g_stamp_.key.clear();
         return 0;

@@ -192,7 +192,8 @@ class Engine {
     const WT* find(const std::string& name);
     void* persistent(size_t bytes, bool zero);
     int ensure_arena();
-    int build_unet_plan(int B, int R);
+    int build_unet_plan(int B, int R, bool shared_input);
+    bool unet_plan_dedup_ = false;
     int build_vae_enc_plan(int Nb, int R);
     int build_vae_dec_plan(int B, int R);
     int build_encoder_plan();
@@ -247,6 +248,7 @@ class Engine {
     std::unordered_map<std::string, FusedShortcut> fused_sc_;
     int opt_fuse_shortcut_ = 1;
     std::unordered_map<std::string, __half*> upconv_w_;
+    int opt_dedup_branches_ = 1;         // layers in front of the first cross-attention once for the uncond and the cond branch
     int opt_fold_downsample_ = 1;        // stride-2 convolutions read the input through parity-view tensor maps (no im2col buffer)
     int opt_fold_upsample_ = 1;          // nearest-2x upsample folded into its convolution (gemm_setup_upconv2x)
     int opt_fold_upsample_rows_ = 3072;  // ... for outputs of at least this many pixels (below, the 16/9 larger folded weights cost more than the multiply-adds save)

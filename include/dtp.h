@@ -180,7 +180,9 @@ int dtp_unet_forward(dtp_handle* h, int B, int R, const float* sample, const flo
  * vae, composite; device time and count accumulated since dtp_set_option("stage_timers", 1)).
  * options: "graph" (CUDA-graph replay of a stamp, default 1), "fold_cross", "fuse_cross" (image-token cross-attention as one
  * launch), "fold_ln" (LayerNorm folded into the consuming contraction), "fold_ln_ff_rows", "fuse_shortcut" (conv_shortcut inside
- * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "splitk_f16" (fp16 partials in the in-kernel split-K reduction; process-wide), "fold_downsample" (stride-2 convolutions
+ * conv2), "fuse_ff_out" (feed-forward output projection folded into the transformer's proj_out), "dedup_branches" (stamp path: the layers in front of the first cross-attention run once for the
+ * uncond and the cond branch, whose sample inputs are identical), "splitk_f16" (fp16 partials in the in-kernel split-K reduction;
+ * process-wide), "fold_downsample" (stride-2 convolutions
  * without an im2col buffer), "fold_upsample" (nearest-2x upsample
  * folded into its 3x3 convolution; "fold_upsample_rows": smallest output pixel count it applies to), "flash", "profile" (per-op events),
  * "stage_timers", "nvtx" (NVTX ranges per stage), "arena_mib" (grow the activation arena to at least this size). */

@@ -198,6 +198,10 @@ if __name__ == "__main__":
                     (3, 16, 16, 1280, 640, 1280), (3, 16, 16, 1280, 2560, 1280), (3, 16, 16, 1280, 1920, 1280),
                     (3, 8, 8, 1280, 2560, 1280)]:
             sweep_conv_sc(*shp)
+    if which == "dedup":  # two sample groups at level 0 (layers in front of the first cross-attention, dedup_branches)
+        for shp in [(8192, 320, 320), (8192, 960, 320)]:
+            sweep_linear(*shp)
+        sweep_conv(2, 64, 64, 320, 320)
     if which in ("all", "vae"):
         for shp in [(2, 512, 512, 128, 128), (2, 256, 256, 256, 256), (2, 128, 128, 512, 512), (1, 512, 512, 256, 128)]:
             sweep_conv(*shp)

@@ -279,6 +279,46 @@ def test_full_e2e_c3_per_gpu(full):
     check_e2e(full, 256, 10, B=4, name="sd15", strict=True, pad=150)
 
 
+def test_full_branch_dedup_matches_three_branch_evaluation(full):
+    """The uncond and the cond branch share their UNet sample input (inpaint_pipeline.py:116-138), so the layers in front of
+    the first cross-attention run once for both (option dedup_branches; needs the fused cross-attention kernel, i.e. the
+    8-head full model). Against the plain three-branch plan on the same stamps, B = 1 and B = 2; dtp_unet_forward with a
+    caller-supplied sample tensor must NOT de-duplicate (its three groups are arbitrary)."""
+    from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
+    R, steps = 256, 4
+    for B in (1, 2):
+        model = TRTConditionalInpainter(R, device=0, model_config=full.cfg, state_dicts=full.sds, max_batch_size=B)
+        model.pipeline.sample_posterior = False
+        model.pipeline.strict_schedule = True
+        model.set_brush(smooth_image(1, 3, R))
+        canvas = make_canvas(B, R)
+        lat = torch.randn(B, 4, R // 8, R // 8, generator=gen(42))
+        settings = dict(steps=steps, context_pad=100, tg_steps=2, width=R, cfg_weight=2.0, tg_weight=1.0)
+        eng = model.engine
+        outs, ops = {}, {}
+        for on in (1, 0):
+            eng.set_option("dedup_branches", on)
+            outs[on] = model.generate_raw(canvas, init_latents=lat, **settings).clone()
+            ops[on] = eng.counter("unet_plan_ops")
+        eng.set_option("dedup_branches", 1)
+        assert ops[1] == ops[0] + 1  # the residual of the first transformer block is expanded to three groups
+        e = rel_l2(outs[1], outs[0])
+        log(f"sd15.branch_dedup.R{R}.B{B}", rel_l2=e)
+        assert e < 2e-3
+        if B == 1:
+            h = R // 8
+            sample = torch.randn(3, 9, h, h, generator=gen(17)).to(DEV)  # three DIFFERENT groups
+            a = eng.unet_forward(sample, 0).clone()
+            assert eng.counter("unet_plan_ops") == ops[0]
+            eng.set_option("dedup_branches", 0)
+            bb = eng.unet_forward(sample, 0).clone()
+            eng.set_option("dedup_branches", 1)
+            assert torch.equal(a, bb)
+        model.pipeline.teardown()
+        del model
+        torch.cuda.empty_cache()
+
+
 def test_graph_replay_and_options_are_equivalent(tiny):
     """CUDA-graph replay, eager launch order, unfolded cross-attention and the materialised-score attention path must all
     produce the same stamp (bit-identical for graph vs eager; <= 2e-3 rel-L2 across algorithmic variants)."""
