@@ -8,6 +8,9 @@ echo "ncu list rc=$?"; wc -l gpurun_out/launches_r2.csv; gzip -f gpurun_out/laun
 for t in memcheck racecheck synccheck; do
   R=64 timeout 900 compute-sanitizer --tool $t --error-exitcode 3 python profiles/sanitize_stamp.py > gpurun_out/sanitizer_$t.log 2>&1; echo "$t rc=$?"; tail -3 gpurun_out/sanitizer_$t.log
 done
+for t in memcheck racecheck; do
+  FULL=1 R=64 timeout 900 compute-sanitizer --tool $t --error-exitcode 3 python profiles/sanitize_stamp.py > gpurun_out/sanitizer_full_$t.log 2>&1; echo "full $t rc=$?"; tail -3 gpurun_out/sanitizer_full_$t.log
+done
 python bench.py > gpurun_out/bench_final_r2.json 2> gpurun_out/bench_final_r2.err; echo "bench rc=$?"
 python bench.py --resolution 256 --denoise-steps 20 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_256.json 2> gpurun_out/bench_r2_256.err; echo "256 rc=$?"
 python bench.py --config c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_c3_1gpu.json 2> gpurun_out/bench_r2_c3_1gpu.err; echo "c3 rc=$?"

@@ -1,10 +1,12 @@
 """One small end-to-end stamp for compute-sanitizer (memcheck / racecheck / synccheck): tiny configuration, B = 2,
 128 x 128, 3 evaluations, eager launches (no graph) so every kernel instantiation the tiny model uses runs under the tool:
 single-CTA and CTA-pair contraction tiles, the in-kernel split-K reduction (tickets, fp16 partials), the folded upsample and
-stride-2 convolutions, the fused cross-attention kernel, flash attention, both GroupNorm kernels (per-group and per-sample
-barrier), canvas pre-process, composite.
+stride-2 convolutions, flash attention, both GroupNorm kernels (per-group and per-sample barrier), canvas pre-process,
+composite. FULL=1 runs one stamp of the full-width model instead (fused cross-attention kernel, branch de-duplication,
+320-wide pair tiles), which the 4-head tiny configuration does not reach.
     compute-sanitizer --tool memcheck  python profiles/sanitize_stamp.py
     compute-sanitizer --tool racecheck python profiles/sanitize_stamp.py
+    FULL=1 R=64 compute-sanitizer --tool memcheck python profiles/sanitize_stamp.py
 """
 import os
 import sys
@@ -17,8 +19,9 @@ from diffusiontexturepainting_b200 import weights as W  # noqa: E402
 from diffusiontexturepainting_b200.testdata import make_canvas, smooth_image  # noqa: E402
 from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter  # noqa: E402
 
-R, B, S = int(os.environ.get("R", "128")), 2, 3
-cfg = W.tiny_config()
+FULL = os.environ.get("FULL", "0") == "1"  # SD-1.5 widths (8 heads): the fused cross-attention kernel, branch de-duplication,
+R, B, S = int(os.environ.get("R", "128")), (1 if FULL else 2), (2 if FULL else 3)  # 320-wide pair tiles; one stamp, two evaluations
+cfg = W.sd15_config() if FULL else W.tiny_config()
 model = TRTConditionalInpainter(R, device=0, model_config=cfg, state_dicts=W.synth_model(cfg), max_batch_size=B)
 model.pipeline.sample_posterior = False
 model.pipeline.strict_schedule = True
