@@ -285,15 +285,17 @@ def test_full_branch_dedup_matches_three_branch_evaluation(full):
     8-head full model). Against the plain three-branch plan on the same stamps, B = 1 and B = 2; dtp_unet_forward with a
     caller-supplied sample tensor must NOT de-duplicate (its three groups are arbitrary)."""
     from diffusiontexturepainting_b200.trt_model import TRTConditionalInpainter
-    R, steps = 256, 4
-    for B in (1, 2):
+    steps = 4
+    # R = 128: the level-0 block has <= 1024 rows, so norm3 is folded too and the cross-attention kernel also emits the row
+    # statistics of its three-group output (separate buffer from the two-group statistics it reads)
+    for R, B in ((256, 1), (256, 2), (128, 1)):
         model = TRTConditionalInpainter(R, device=0, model_config=full.cfg, state_dicts=full.sds, max_batch_size=B)
         model.pipeline.sample_posterior = False
         model.pipeline.strict_schedule = True
         model.set_brush(smooth_image(1, 3, R))
         canvas = make_canvas(B, R)
         lat = torch.randn(B, 4, R // 8, R // 8, generator=gen(42))
-        settings = dict(steps=steps, context_pad=100, tg_steps=2, width=R, cfg_weight=2.0, tg_weight=1.0)
+        settings = dict(steps=steps, context_pad=R // 3, tg_steps=2, width=R, cfg_weight=2.0, tg_weight=1.0)
         eng = model.engine
         outs, ops = {}, {}
         for on in (1, 0):
@@ -305,7 +307,7 @@ def test_full_branch_dedup_matches_three_branch_evaluation(full):
         e = rel_l2(outs[1], outs[0])
         log(f"sd15.branch_dedup.R{R}.B{B}", rel_l2=e)
         assert e < 2e-3
-        if B == 1:
+        if B == 1 and R == 256:
             h = R // 8
             sample = torch.randn(3, 9, h, h, generator=gen(17)).to(DEV)  # three DIFFERENT groups
             a = eng.unet_forward(sample, 0).clone()
