@@ -191,3 +191,55 @@ def test_resize_fold_algebra():
                 src = views[(py, px)][:, :, 1 + sy:1 + sy + Ho, 1 + sx:1 + sx + Wo]
                 acc = acc + torch.einsum("oc,nchw->nohw", w[:, :, ky, kx], src)
         assert torch.allclose(acc, ref2, atol=1e-12)
+
+
+def test_header_is_plain_c_and_a_c_host_gets_a_clean_error_without_a_gpu(tmp_path):
+    """The boundary is a C ABI: include/dtp.h must compile as C99 (and C++17) on its own, a C host must link against the
+    library, and on a machine without an sm_100 device dtp_create must FAIL WITH A MESSAGE (no crash, no silent fallback)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    inc = os.path.join(ROOT, "include")
+    for std, lang in (("-std=c99", "c"), ("-std=c++17", "c++")):
+        r = subprocess.run([cc, "-x", lang, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc,
+                            os.path.join(inc, "dtp.h")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    from diffusiontexturepainting_b200 import _native as nat
+    lib = nat.library_path() if hasattr(nat, "library_path") else os.path.join(ROOT, "diffusiontexturepainting_b200", "libdtp_sm100.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "dtp.h"
+int main(void) {
+    dtp_config cfg;
+    dtp_handle* h = NULL;
+    int rc;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.unet_in_channels = 9; cfg.unet_out_channels = 4;
+    cfg.unet_block_out[0] = 64; cfg.unet_block_out[1] = 128; cfg.unet_block_out[2] = 256; cfg.unet_block_out[3] = 256;
+    cfg.unet_down_attn[0] = cfg.unet_down_attn[1] = cfg.unet_down_attn[2] = 1;
+    cfg.unet_layers_per_block = 2; cfg.unet_heads = 4; cfg.unet_cross_dim = 128; cfg.groups = 32;
+    cfg.vae_block_out[0] = 64; cfg.vae_block_out[1] = 64; cfg.vae_block_out[2] = 128; cfg.vae_block_out[3] = 128;
+    cfg.vae_layers_per_block = 2; cfg.vae_latent = 4;
+    cfg.enc_width = 128; cfg.enc_layers = 2; cfg.enc_heads = 2; cfg.enc_mlp = 256; cfg.enc_tower_layers = 2;
+    cfg.enc_tower_heads = 4; cfg.enc_cross_dim = 128; cfg.enc_tokens = 14; cfg.arena_bytes = 1u << 20;
+    rc = dtp_create(&cfg, &h);
+    printf("rc=%d handle=%s msg=%s\n", rc, h ? "set" : "null", dtp_last_error(h));
+    if (h) dtp_destroy(h);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    r = subprocess.run([cc, "-std=c99", "-I", inc, str(src), "-o", str(exe), lib, "-Wl,-rpath," + os.path.dirname(lib)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    if not torch.cuda.is_available():
+        assert "rc=-" in r.stdout and "handle=null" in r.stdout, r.stdout
+        assert "msg=" in r.stdout and len(r.stdout.split("msg=")[1].strip()) > 8, r.stdout  # a reason, not an empty string
