@@ -16,6 +16,11 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-DDTP_BUILD",
 ]
+# Developer knob: DTP_SPLIT_COMPILE=1 adds nvcc's -split-compile=0 (the 29 instantiations of the contraction kernel compile in
+# ~55 s instead of ~190 s on 8 cores). Off by default: spill decisions differ slightly, and every number under profiles/ was
+# measured with the default build.
+if os.environ.get("DTP_SPLIT_COMPILE", "0") == "1":
+    NVCC_FLAGS.append("-split-compile=0")
 
 
 def _sources():
